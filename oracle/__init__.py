@@ -1,0 +1,163 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loaders for the CPU oracle and the compiled reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package. The product (jampack_b200/) never does.
+
+  port()  -> oracle/_build/libjporacle.so : our C restatement (bwt_oracle.c) + generators (gen.c)
+  ref()   -> oracle/_ref/libjamref.so     : the UNMODIFIED reference BWT stage (bwt.cpp + divsufsort.cpp
+             + format.cpp + sys_detect.cpp of /root/reference) behind oracle/ref_wrap.cpp, or None if it
+             was never built (it is built in the authoring container and travels to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+UNITS = 120  # format.hpp:26
+TRAILER = UNITS * 4
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+
+def _ptr(a, t=_u8p):
+    return a.ctypes.data_as(t)
+
+
+def build(reference_dir="/root/reference"):
+    """Compile the oracle (always) and oracle/_ref (only where the reference sources exist)."""
+    targets = ["oracle"]
+    if os.path.isfile(os.path.join(reference_dir, "bwt.cpp")):
+        targets.append("ref")
+    subprocess.run(["make", "-s", "-C", HERE, f"REF={reference_dir}"] + targets, check=True)
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        path = os.path.join(HERE, "_build", "libjporacle.so")
+        if not os.path.isfile(path):
+            build()
+        L = C.CDLL(path)
+        L.jpo_bwt_forward.argtypes = [_u8p, C.c_int32, _u8p, _i32p]
+        L.jpo_bwt_forward.restype = C.c_int
+        L.jpo_bwt_inverse.argtypes = [_u8p, C.c_int32, _u8p, _i32p, C.c_int]
+        L.jpo_bwt_inverse.restype = C.c_int
+        L.jpo_build_map.argtypes = [_u8p, C.c_int32, C.c_int32, _i32p, _i32p]
+        L.jpo_build_map.restype = C.c_int
+        L.jpo_suffix_array_export.argtypes = [_u8p, _i32p, C.c_int32]
+        L.jpo_suffix_array_export.restype = C.c_int
+        L.jpo_check_suffix_array.argtypes = [_u8p, _i32p, C.c_int32]
+        L.jpo_check_suffix_array.restype = C.c_int
+        for name in ("uniform", "markov2", "repetitive"):
+            f = getattr(L, "jpo_gen_" + name)
+            f.argtypes = [_u8p, C.c_int64, C.c_uint64]
+            f.restype = None
+        for name in ("alla", "kat_quadratic", "kat_extremes"):
+            f = getattr(L, "jpo_gen_" + name)
+            f.argtypes = [_u8p, C.c_int64]
+            f.restype = None
+        L.jpo_fnv1a64.argtypes = [_u8p, C.c_int64]
+        L.jpo_fnv1a64.restype = C.c_uint64
+        _port = L
+    return _port
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        path = os.path.join(HERE, "_ref", "libjamref.so")
+        if not os.path.isfile(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_bwt_forward.argtypes = [_u8p, C.c_int, _u8p, _i32p]
+        L.ref_bwt_forward.restype = C.c_int
+        L.ref_bwt_inverse.argtypes = [_u8p, C.c_int, _u8p, _i32p, C.c_int, _i32p]
+        L.ref_bwt_inverse.restype = C.c_int
+        pp = C.POINTER(C.c_void_p)
+        L.ref_bwt_forward_batch.argtypes = [pp, _i32p, pp, C.c_int, C.c_int]
+        L.ref_bwt_forward_batch.restype = C.c_double
+        L.ref_bwt_inverse_batch.argtypes = [pp, _i32p, pp, C.c_int, C.c_int, C.c_int]
+        L.ref_bwt_inverse_batch.restype = C.c_double
+        L.ref_core_count.restype = C.c_int
+        _ref = L
+    return _ref
+
+
+# ---- generators ----------------------------------------------------------
+def gen(kind, n, seed=0):
+    """kind in uniform|markov2|repetitive|alla|kat_quadratic|kat_extremes -> np.uint8[n]"""
+    T = np.empty(int(n), dtype=np.uint8)
+    if n == 0:
+        return T
+    L = port()
+    if kind in ("uniform", "markov2", "repetitive"):
+        getattr(L, "jpo_gen_" + kind)(_ptr(T), int(n), int(seed))
+    else:
+        getattr(L, "jpo_gen_" + kind)(_ptr(T), int(n))
+    return T
+
+
+def fnv(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return int(port().jpo_fnv1a64(_ptr(a), a.size))
+
+
+# ---- stage calls; `impl` is "port" or "ref" -------------------------------------------------------
+def forward(T, impl="port", prefill=0):
+    """-> np.uint8[len+480]; the trailer keeps `prefill` bytes when nlen == 0 (bwt.cpp:35)."""
+    T = np.ascontiguousarray(T, dtype=np.uint8)
+    out = np.full(T.size + TRAILER, prefill, dtype=np.uint8)
+    ol = C.c_int32(0)
+    if impl == "ref":
+        rc = ref().ref_bwt_forward(_ptr(T), T.size, _ptr(out), C.byref(ol))
+    else:
+        rc = port().jpo_bwt_forward(_ptr(T), T.size, _ptr(out), C.byref(ol))
+    if rc != 0:
+        raise RuntimeError(f"oracle forward rc={rc}")
+    assert ol.value == T.size + TRAILER
+    return out
+
+
+def inverse(B, impl="port", units=120, threads=1):
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    out = np.zeros(max(B.size - TRAILER, 0), dtype=np.uint8)
+    ol = C.c_int32(0)
+    if impl == "ref":
+        after = C.c_int32(0)
+        rc = ref().ref_bwt_inverse(_ptr(B), B.size, _ptr(out), C.byref(ol), threads, C.byref(after))
+        assert after.value == B.size - TRAILER  # bwt.cpp:77 mutates *Input.size
+    else:
+        rc = port().jpo_bwt_inverse(_ptr(B), B.size, _ptr(out), C.byref(ol), units)
+    if rc != 0:
+        raise RuntimeError(f"oracle inverse rc={rc}")
+    assert ol.value == B.size - TRAILER
+    return out
+
+
+def indices(B):
+    """The 120 sampled primary indices stored after the raw tail (bwt.cpp:57-61)."""
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    return np.frombuffer(B[B.size - TRAILER:].tobytes(), dtype="<i4").copy()
+
+
+def build_map(B, nlen, idx):
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    M = np.empty(nlen, dtype=np.int32)
+    Ct = np.empty(257, dtype=np.int32)
+    port().jpo_build_map(_ptr(B), nlen, idx, _ptr(M, _i32p), _ptr(Ct, _i32p))
+    return M, Ct
+
+
+def suffix_array(T):
+    T = np.ascontiguousarray(T, dtype=np.uint8)
+    SA = np.empty(T.size, dtype=np.int32)
+    rc = port().jpo_suffix_array_export(_ptr(T), _ptr(SA, _i32p), T.size)
+    assert rc == 0
+    return SA
