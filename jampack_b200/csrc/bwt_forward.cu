@@ -1,0 +1,420 @@
+// bwt_forward.cu -- forward BWT for sm_100a: GPU suffix sort + BWT emission + the 120 sampled indices.
+//
+// Replaces BlockSort::Bwt::ForwardBwt (reference bwt.cpp:22-65) and the divsufsort() call under it
+// (divsufsort.cpp:1721; contract divsufsort.hpp:37-45: plain suffix array, a proper prefix sorts first).
+// Nothing of divsufsort's induced-copying design is kept: a serial induce pass has no place on 148 SMs.
+//
+//   1. symbol remap   present byte values -> dense codes 1..sigma (0 = end of string), b = ceil(log2(sigma+1)) bits
+//   2. initial keys   key(i) = the first d = floor(64/b) codes of suffix i, zero padded: the padding IS the
+//                     sentinel, so "shorter sorts first" needs no tie-break and no suffix shorter than the
+//                     current depth is ever in a group with another one
+//   3. radix bucket   LSD radix sort of (key, i)                                      [radix_sort.cuh]
+//   4. ranks          group heads = key changes; rank = 1 + position of the group's head; singletons retire
+//                     into SA at once, the rest are compacted into the active set
+//   5. doubling       while any group is unsorted: key = (dense group id, ISA[s + h]) -> radix sort ->
+//                     heads/ranks/retire/compact; h doubles. Only the active set is touched (Larsson-Sadakane
+//                     discarding); ISA[nlen] = 0 is the empty suffix.
+//   6. emit           bwt[o] = T[SA[row]-1] with the row of suffix 0 skipped (bwt.cpp:50-56), the sampled
+//                     indices ISA[k*step] (bwt.cpp:44-48,57-61), the raw tail (bwt.cpp:32-33).
+#include "bwt_internal.cuh"
+#include "radix_sort.cuh"
+
+namespace jp {
+
+struct FwdMeta {
+	u32 code[256];
+	i32 sigma, bits, depth;
+	u32 hist[256];
+};
+
+// ---- 1. symbol histogram and dense codes -------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fwd_symhist(const u8* __restrict__ T, i32 n, FwdMeta* __restrict__ meta)
+{
+	__shared__ u32 h[8][256];
+	const int t = threadIdx.x, w = t >> 5;
+	for (int i = t; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+	__syncthreads();
+	const i64 stride = (i64)gridDim.x * 256 * 16;
+	for (i64 p = ((i64)blockIdx.x * 256 + t) * 16; p < n; p += stride) {
+		if (p + 16 <= n) {
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(T + p));
+			const u32 wd[4] = {q.x, q.y, q.z, q.w};
+			#pragma unroll
+			for (int k = 0; k < 16; k++) atomicAdd(&h[w][(wd[k >> 2] >> ((k & 3) * 8)) & 255], 1u);
+		} else for (i64 q = p; q < n; q++) atomicAdd(&h[w][T[q]], 1u);
+	}
+	__syncthreads();
+	u32 s = 0;
+	#pragma unroll
+	for (int k = 0; k < 8; k++) s += h[k][t];
+	if (s) atomicAdd(&meta->hist[t], s);
+}
+
+__global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
+{
+	__shared__ u32 ws[32];
+	const int t = threadIdx.x;
+	const u32 present = meta->hist[t] ? 1u : 0u;
+	u32 total;
+	const u32 inc = block_incl_sum(present, ws, &total);
+	meta->code[t] = present ? inc : 0u;            // codes 1..sigma in byte order
+	if (t == 0) {
+		const int bits = bit_length((u64)total);   // codes 0..sigma need bit_length(sigma) bits
+		meta->sigma = (i32)total;
+		meta->bits = bits;
+		meta->depth = 64 / bits;
+	}
+}
+
+// ---- 2. initial keys -------------------------------------------------------------------------------
+constexpr int KEY_TILE = 2048;
+__global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 n, const FwdMeta* __restrict__ meta,
+                                                  u64* __restrict__ keys, u32* __restrict__ vals)
+{
+	__shared__ u16 sc[KEY_TILE + 64];
+	__shared__ u16 code[256];
+	const int t = threadIdx.x;
+	code[t] = (u16)meta->code[t];
+	const int bits = meta->bits, depth = meta->depth;
+	__syncthreads();
+	const i64 base = (i64)blockIdx.x * KEY_TILE;
+	for (int i = t; i < KEY_TILE + 64; i += 256) {
+		const i64 p = base + i;
+		sc[i] = p < n ? code[T[p]] : (u16)0;
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int j = 0; j < KEY_TILE / 256; j++) {
+		const int li = j * 256 + t;
+		const i64 p = base + li;
+		if (p < n) {
+			u64 k = 0;
+			for (int d = 0; d < depth; d++) k = (k << bits) | sc[li + d];
+			keys[p] = k;
+			vals[p] = (u32)p;
+		}
+	}
+}
+
+// ---- 4/5. group heads -> ranks, retire singletons, compact the rest ----------------------------------
+// Scan element: (P of the last group head so far, #survivors, #surviving group heads).
+constexpr int GS_THREADS = 256;
+constexpr int GS_SUB     = 16;
+constexpr int GS_TILE    = GS_THREADS * GS_SUB;
+struct GAgg { i32 mh; u32 ns; u32 ng; u32 pad; };
+
+struct GFlags { bool head, nhead; };
+__device__ __forceinline__ GFlags group_flags(const u64* __restrict__ K, u32 j, u32 A)
+{
+	const u64 kj = K[j];
+	GFlags f;
+	f.head = (j == 0) || (K[j - 1] != kj);
+	f.nhead = (j + 1 == A) || (K[j + 1] != kj);
+	return f;
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict__ K, const u32* __restrict__ P, u32 A,
+                                                           GAgg* __restrict__ agg)
+{
+	__shared__ i32 smh[8];
+	__shared__ u32 sns[8], sng[8];
+	const int t = threadIdx.x;
+	const u32 base = blockIdx.x * GS_TILE;
+	i32 mh = -1; u32 ns = 0, ng = 0;
+	#pragma unroll 4
+	for (int s = 0; s < GS_SUB; s++) {
+		const u32 j = base + s * GS_THREADS + t;
+		if (j < A) {
+			const GFlags f = group_flags(K, j, A);
+			if (f.head) mh = max(mh, (i32)(P ? P[j] : j));
+			ns += !(f.head && f.nhead);
+			ng += (f.head && !f.nhead);
+		}
+	}
+	mh = warp_max(mh); ns = warp_sum(ns); ng = warp_sum(ng);
+	if ((t & 31) == 0) { smh[t >> 5] = mh; sns[t >> 5] = ns; sng[t >> 5] = ng; }
+	__syncthreads();
+	if (t == 0) {
+		for (int k = 1; k < 8; k++) { mh = max(mh, smh[k]); ns += sns[k]; ng += sng[k]; }
+		GAgg a; a.mh = mh; a.ns = ns; a.ng = ng; a.pad = 0;
+		agg[blockIdx.x] = a;
+	}
+}
+
+// single block: exclusive scan of the tile aggregates in place; totals -> out[0] = survivors, out[1] = groups
+__global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg, int tiles, u32* __restrict__ out)
+{
+	__shared__ i32 wmh[32];
+	__shared__ u32 wns[32], wng[32];
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const int per = (tiles + 1023) / 1024;
+	const int lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	i32 mh = -1; u32 ns = 0, ng = 0;
+	for (int k = lo; k < hi; k++) { const GAgg a = agg[k]; mh = max(mh, a.mh); ns += a.ns; ng += a.ng; }
+	// inclusive scan across threads
+	const i32 imh = warp_incl_max(mh); const u32 ins = warp_incl_sum(ns), ing = warp_incl_sum(ng);
+	if (lane == 31) { wmh[w] = imh; wns[w] = ins; wng[w] = ing; }
+	__syncthreads();
+	i32 pmh = -1; u32 pns = 0, png = 0;           // aggregate of all earlier warps
+	for (int k = 0; k < w; k++) { pmh = max(pmh, wmh[k]); pns += wns[k]; png += wng[k]; }
+	// exclusive prefix for this thread
+	i32 emh = __shfl_up_sync(0xffffffffu, imh, 1); u32 ens = __shfl_up_sync(0xffffffffu, ins, 1), eng = __shfl_up_sync(0xffffffffu, ing, 1);
+	if (lane == 0) { emh = -1; ens = 0; eng = 0; }
+	emh = max(emh, pmh); ens += pns; eng += png;
+	for (int k = lo; k < hi; k++) {
+		const GAgg a = agg[k];
+		GAgg e; e.mh = emh; e.ns = ens; e.ng = eng; e.pad = 0;
+		agg[k] = e;
+		emh = max(emh, a.mh); ens += a.ns; eng += a.ng;
+	}
+	if (t == 1023) { out[0] = pns + ins; out[1] = png + ing; }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict__ K, const u32* __restrict__ V,
+                                                          const u32* __restrict__ P, u32 A, const GAgg* __restrict__ agg,
+                                                          int rank_bits, u32* __restrict__ ISA, u32* __restrict__ SA,
+                                                          u64* __restrict__ Kn, u32* __restrict__ Vn, u32* __restrict__ Pn)
+{
+	__shared__ i32 wmh[8];
+	__shared__ u32 wcnt[8];
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const u32 base = blockIdx.x * GS_TILE;
+	const GAgg carry0 = agg[blockIdx.x];
+	i32 cmh = carry0.mh; u32 cns = carry0.ns, cng = carry0.ng;
+	for (int s = 0; s < GS_SUB; s++) {
+		const u32 j = base + s * GS_THREADS + t;
+		if (base + s * GS_THREADS >= A) break;          // uniform across the block
+		bool head = false, surv = false, shead = false;
+		u32 v = 0, p = 0;
+		if (j < A) {
+			const GFlags f = group_flags(K, j, A);
+			head = f.head; surv = !(f.head && f.nhead); shead = f.head && !f.nhead;
+			v = V[j]; p = P ? P[j] : j;
+		}
+		const i32 mh = head ? (i32)p : -1;
+		const u32 packed = (surv ? 1u : 0u) | (shead ? 0x10000u : 0u);
+		i32 imh = warp_incl_max(mh);
+		u32 ipk = warp_incl_sum(packed);
+		if (lane == 31) { wmh[w] = imh; wcnt[w] = ipk; }
+		__syncthreads();
+		i32 pmh = cmh; u32 ppk = 0, tpk = 0;
+		i32 tmh = cmh;
+		#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const i32 a = wmh[k]; const u32 b = wcnt[k];
+			if (k < w) { pmh = max(pmh, a); ppk += b; }
+			tmh = max(tmh, a); tpk += b;
+		}
+		imh = max(imh, pmh);
+		ipk += ppk;
+		if (j < A) {
+			const u32 ns_incl = cns + (ipk & 0xffffu);
+			const u32 ng_incl = cng + (ipk >> 16);
+			ISA[v] = (u32)imh + 1u;
+			if (surv) {
+				const u32 q = ns_incl - 1;
+				Vn[q] = v; Pn[q] = p; Kn[q] = (u64)(ng_incl - 1) << rank_bits;
+			} else SA[p] = v;
+		}
+		cmh = tmh; cns += tpk & 0xffffu; cng += tpk >> 16;
+		__syncthreads();
+	}
+}
+
+// ---- 5. doubling: fetch the rank of the continuation ---------------------------------------------------
+__global__ void __launch_bounds__(256) k_fwd_gather(u64* __restrict__ K, const u32* __restrict__ V, u32 A,
+                                                    const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err)
+{
+	const u32 j = blockIdx.x * 256 + threadIdx.x;
+	if (j >= A) return;
+	u32 p = V[j] + h;
+	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+	K[j] |= (u64)__ldg(&ISA[p]);
+}
+
+// ---- 6. emission ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fwd_emit(const u8* __restrict__ T, const u32* __restrict__ SA,
+                                                  const u32* __restrict__ ISA, i32 n, u8* __restrict__ out)
+{
+	const i64 o0 = ((i64)blockIdx.x * 256 + threadIdx.x) * 4;
+	if (o0 >= n) return;
+	const i64 idx0 = (i64)ISA[0] - 1;                 // SA position of suffix 0 (bwt.cpp:51)
+	u32 acc = 0; int cnt = 0;
+	#pragma unroll
+	for (int b = 0; b < 4; b++) {
+		const i64 o = o0 + b;
+		if (o < n) {
+			u32 c;
+			if (o == 0) c = T[n - 1];                 // bwt.cpp:50
+			else {
+				const i64 i = (o <= idx0) ? o - 1 : o; // bwt.cpp:53-56
+				c = T[SA[i] - 1];
+			}
+			acc |= c << (8 * b); cnt++;
+		}
+	}
+	if (cnt == 4) *reinterpret_cast<u32*>(out + o0) = acc;
+	else for (int b = 0; b < cnt; b++) out[o0 + b] = (u8)(acc >> (8 * b));
+}
+
+__global__ void k_fwd_trailer(const u8* __restrict__ T, const u32* __restrict__ ISA, i32 n, i32 len, u8* __restrict__ out)
+{
+	const int t = threadIdx.x;
+	const i32 step = n / JP_BWT_UNITS;                 // bwt.cpp:44
+	if (t < JP_BWT_UNITS) {
+		const u32 v = ISA[(i64)t * step];              // = Indicies[t] + 1 (bwt.cpp:46-48,57-58)
+		u8* p = out + len + 4 * t;                     // unaligned, native-endian (bwt.cpp:60-61)
+		p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24);
+	}
+	for (int i = t; i < len - n; i += blockDim.x) out[n + i] = T[n + i];   // bwt.cpp:32-33
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------
+struct FwdBuffers {
+	RadixBuffers rb;
+	u32* P[2];
+	u32* ISA; u32* SA;
+	GAgg* agg;
+	FwdMeta* meta;
+	u32* counters;
+	int* err;
+};
+
+static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
+{
+	const size_t N = (size_t)n;
+	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
+	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + Arena::align(N * 4) +
+	               Arena::align(rtiles * 256 * 4) + Arena::align(256 * 4) + Arena::align(gtiles * sizeof(GAgg)) +
+	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64);
+	JP_TRY(arena_reserve(c, total));
+	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
+	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
+	b.P[0] = arena_take<u32>(c, N); b.P[1] = arena_take<u32>(c, N);
+	b.ISA = arena_take<u32>(c, N + 1); b.SA = arena_take<u32>(c, N);
+	b.rb.tile_hist = arena_take<u32>(c, rtiles * 256);
+	b.rb.totals = arena_take<u32>(c, 256);
+	b.agg = arena_take<GAgg>(c, gtiles);
+	b.meta = arena_take<FwdMeta>(c, 1);
+	b.counters = arena_take<u32>(c, 16);
+	b.err = arena_take<int>(c, 16);
+	return JP_OK;
+}
+
+// One grouping step over the sorted pairs in rb.k/v[cur]; survivors land in rb.k/v[cur^1] and P[pc^1].
+static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos, u32 A, int rank_bits, cudaStream_t s)
+{
+	const int tiles = (int)((A + GS_TILE - 1) / GS_TILE);
+	const u32* P = identity_pos ? nullptr : b.P[pc];
+	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], P, A, b.agg); JP_LAUNCH(c);
+	k_grp_scan_tiles<<<1, 1024, 0, s>>>(b.agg, tiles, b.counters); JP_LAUNCH(c);
+	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, b.SA,
+	                                          b.rb.k[cur ^ 1], b.rb.v[cur ^ 1], b.P[pc ^ 1]); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaMemcpyAsync(c.h_small + 8, b.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	return JP_OK;
+}
+
+// Builds SA and ISA (ranks 1..n; ISA[n] = 0) of T[0..n) in b. Events ev[1..4] mark the phase boundaries.
+static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t s, jp_bwt_stats* st)
+{
+	JP_CUDA(cudaMemsetAsync(b.meta, 0, sizeof(FwdMeta), s));
+	JP_CUDA(cudaMemsetAsync(b.err, 0, 64, s));
+	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
+	const i64 hwant = ((i64)n + 4095) / 4096, hcap = (i64)c.sm_count * 8;
+	const int hblocks = (int)(hwant < hcap ? hwant : hcap);
+	k_fwd_symhist<<<hblocks, 256, 0, s>>>(d_T, n, b.meta); JP_LAUNCH(c);
+	k_fwd_codes<<<1, 256, 0, s>>>(b.meta); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 3 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth
+	JP_CUDA(cudaStreamSynchronize(s));
+	const int bits = c.h_small[17], depth = c.h_small[18];
+	if (bits < 1 || bits > 9 || depth < 7 || depth > 64) { set_error_detail("symbol remap gave bits=%d depth=%d", bits, depth); return JP_ERR_INTERNAL; }
+	st->symbol_bits = bits; st->initial_depth = depth;
+
+	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0]); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[1], s));
+	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, bits * depth, s, &c.launches);
+	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[2], s));
+
+	const int rank_bits = bit_length((u64)n);
+	int pc = 0;
+	JP_TRY(group_step(c, b, cur, pc, true, (u32)n, rank_bits, s));
+	JP_CUDA(cudaEventRecord(c.ev[3], s));
+	int act = cur ^ 1; pc ^= 1;
+	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
+	u64 sectors = 2ull * (u64)n;
+	i64 h = depth;
+	int rounds = 0;
+	while (A > 0) {
+		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
+		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
+		st->active_fraction[rounds] = (float)((double)A / (double)n);
+		sectors += 2ull * A;
+		k_fwd_gather<<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err); JP_LAUNCH(c);
+		const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
+		cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
+		if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+		JP_TRY(group_step(c, b, cur, pc, false, A, rank_bits, s));
+		act = cur ^ 1; pc ^= 1;
+		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
+		h *= 2; rounds++;
+	}
+	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
+	JP_CUDA(cudaEventRecord(c.ev[4], s));
+	st->rounds = rounds;
+	st->random_sectors = sectors;
+	return JP_OK;
+}
+
+int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, jp_bwt_stats* st)
+{
+	const i32 nlen = len - len % JP_BWT_UNITS;                          // bwt.cpp:29-30
+	st->direction = 0; st->len = len; st->nlen = nlen; st->device = c.device;
+	JP_CUDA(cudaEventRecord(c.ev[0], s));
+	if (nlen == 0) {                                                    // bwt.cpp:35: tail only, trailer untouched
+		if (len > 0) JP_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)len, cudaMemcpyDeviceToDevice, s));
+		JP_CUDA(cudaEventRecord(c.ev[1], s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[1]));
+		return JP_OK;
+	}
+	FwdBuffers b;
+	JP_TRY(fwd_alloc(c, nlen, b));
+	JP_TRY(suffix_sort(c, d_in, nlen, b, s, st));
+	k_fwd_emit<<<(int)(((i64)nlen + 1023) / 1024), 256, 0, s>>>(d_in, b.SA, b.ISA, nlen, d_out); JP_LAUNCH(c);
+	k_fwd_trailer<<<1, 128, 0, s>>>(d_in, b.ISA, nlen, len, d_out); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[5], s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	for (int i = 0; i < 5; i++) JP_CUDA(cudaEventElapsedTime(&st->ms_phase[i], c.ev[i], c.ev[i + 1]));
+	JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[5]));
+	st->device_bytes = c.arena.high;
+	return JP_OK;
+}
+
+int debug_suffix_array(Ctx& c, const u8* h_in, i32 n, i32* h_sa)
+{
+	if (n == 0) return JP_OK;
+	cudaStream_t s = c.own_stream;
+	c.arena.reset();
+	FwdBuffers b;
+	const size_t N = (size_t)n;
+	JP_TRY(arena_reserve(c, N * 48 + (8u << 20)));
+	u8* d_T = arena_take<u8>(c, N + 16);
+	JP_TRY(fwd_alloc(c, n, b));
+	JP_CUDA(cudaMemcpyAsync(d_T, h_in, N, cudaMemcpyHostToDevice, s));
+	JP_CUDA(cudaEventRecord(c.ev[0], s));
+	jp_bwt_stats st = {};
+	JP_TRY(suffix_sort(c, d_T, n, b, s, &st));
+	JP_CUDA(cudaMemcpyAsync(h_sa, b.SA, N * 4, cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	return JP_OK;
+}
+
+} // namespace jp

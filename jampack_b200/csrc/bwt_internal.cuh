@@ -1,0 +1,58 @@
+// bwt_internal.cuh -- per-call context (device, stream, workspace arena) shared by the forward and
+// inverse drivers and the C-ABI in jp_bwt_api.cu.
+#pragma once
+#include "common.cuh"
+#include "../../include/jp_bwt.h"
+
+namespace jp {
+
+// Grow-only bump arena: one cudaMalloc per context, re-used by every call that borrows the context
+// (cudaMalloc of gigabytes costs milliseconds; a block stage is called once per block).
+struct Arena {
+	u8*    base = nullptr;
+	size_t cap = 0, off = 0, high = 0;
+	void reset() { off = 0; }
+	static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
+};
+
+struct Ctx {
+	int          device = -1;
+	cudaStream_t own_stream = nullptr;
+	Arena        arena;
+	int*         h_small = nullptr;   // pinned: error flag + counters read back per round (64 ints)
+	u8*          h_stage[2] = {nullptr, nullptr}; // pinned staging for pageable host blocks
+	size_t       h_stage_cap = 0;
+	u8*          d_in = nullptr;      // device copies of the caller's host blocks (host entry points)
+	u8*          d_out = nullptr;
+	size_t       d_io_cap = 0;
+	cudaEvent_t  ev[12] = {};
+	int          launches = 0;
+	int          sm_count = 0;
+	bool         busy = false;
+};
+
+// Reserve `total` bytes up front (re-allocating the arena if it is too small), then carve.
+int arena_reserve(Ctx& c, size_t total);
+template <typename T> inline T* arena_take(Ctx& c, size_t count)
+{
+	size_t bytes = Arena::align(count * sizeof(T));
+	T* p = (T*)(c.arena.base + c.arena.off);
+	c.arena.off += bytes;
+	if (c.arena.off > c.arena.high) c.arena.high = c.arena.off;
+	return p;
+}
+
+#define JP_LAUNCH(ctx) (++(ctx).launches)
+#define JP_KCHECK() JP_CUDA(cudaGetLastError())
+
+int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st);
+int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, jp_bwt_stats* st);
+
+// test hooks
+int debug_lf(Ctx& c, const u8* h_in, i32 nlen, i32* h_lf, i32* h_ctable);
+int debug_suffix_array(Ctx& c, const u8* h_in, i32 n, i32* h_sa);
+double debug_gather_rate(Ctx& c, u64 table_bytes, i32 chains, i32 steps, int dependent);
+
+int map_dev_err(int de);
+
+} // namespace jp

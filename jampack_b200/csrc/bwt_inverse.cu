@@ -1,0 +1,612 @@
+// bwt_inverse.cu -- inverse BWT for sm_100a.
+//
+// Replaces BlockSort::Bwt::InverseBwt (reference bwt.cpp:72-282): byte histogram + C table
+// (bwt.cpp:141-169), the LF/rank table (the inverse permutation of the reference's Map, bwt.cpp:171-174)
+// and the multi-index walk (bwt.cpp:176-183, :261-275) -- restructured for a machine that needs
+// >= 10^4 loads in flight rather than 120 (SURVEY.md finding 5, Appendix D):
+//
+//   rows        the nlen+1 rows of the sentinel-inclusive BWT matrix; row 0 is the empty suffix, row idx
+//               (= stored index 0) is suffix 0, whose L symbol is the dropped '$'. Byte i of the stored
+//               BWT belongs to row i + (i >= idx).
+//   lf[i]       = 1 + C[bwt[i]] + #{j < i : bwt[j] == bwt[i]} : the row of the suffix one position to the
+//               left. The symbol stepped over is NOT fetched from the BWT: it is the F-column symbol of
+//               lf[i], found in the 257-entry C table (shared memory). One random 32 B sector per byte.
+//   marks       bit 31 of lf[i] (row numbers need <= 31 bits, format.hpp:22) flags row(i) as the start of a
+//               sub-chain: one pseudo-random row in every window of m rows, plus the 120 rows the stored
+//               indices name (text positions k*step) and row 0 (text position nlen).
+//   pass 1      one walker per sub-chain start: walk left until the next mark; record (next start, length).
+//   ranking     asynchronous pointer jumping over the (next, length) records; the 121 anchors absorb. Every
+//               sub-chain learns which decode unit it belongs to and its offset from that unit's start, so all
+//               120 decode units of the format run concurrently, each cut into ~step/m independent pieces.
+//   pass 2      the same walk again, now writing bytes right-to-left at the known text offset, packed into
+//               aligned 32-bit stores.
+//
+// Device memory: caller's in (N+480) + out (N) + lf (4N) = 6N, plus o(N): 8 B per sub-chain (N/8 at m = 64)
+// and 1 KiB per 64 KiB tile (N/64).
+#include "bwt_internal.cuh"
+
+namespace jp {
+
+constexpr int  INV_THREADS    = 256;
+constexpr int  INV_WARPS      = INV_THREADS / 32;
+constexpr int  INV_TILE       = 65536;          // bytes per histogram / LF tile
+constexpr int  INV_CHUNK      = INV_WARPS * 512; // bytes ranked per block iteration of the LF build
+constexpr u32  LF_MARK        = 0x80000000u;
+constexpr u32  LF_MASK        = 0x7fffffffu;
+constexpr int  N_ANCHOR       = JP_BWT_UNITS + 1; // anchor k = row of text position k*step, k = 0..120
+constexpr u32  REC_INVALID    = 0xffffffffu;
+constexpr int  RANK_HOP_CAP   = 1 << 22;
+
+struct InvMeta {
+	i32 idx;                       // stored index 0 = row of suffix 0
+	i32 anchor_row[N_ANCHOR];      // [0] = idx (terminal), [k] = stored index k, [120] = 0
+	i32 sorted_row[N_ANCHOR];      // anchor rows ascending ...
+	i32 sorted_id[N_ANCHOR];       // ... and which anchor each one is
+	i32 ctable[257];               // C[c] = #{bytes < c}; C[256] = nlen
+};
+
+// ---- prepare: read + validate the 120 stored indices, sort the anchors, copy the raw tail ---------
+// bwt.cpp:80-89. The trailer sits at byte offset Len, unaligned, native-endian (little on every CUDA host).
+__global__ void k_inv_prepare(const u8* __restrict__ in, i32 len, i32 nlen, u8* __restrict__ out,
+                              InvMeta* __restrict__ meta, int* __restrict__ err)
+{
+	__shared__ i32 row[N_ANCHOR];
+	const int t = threadIdx.x;
+	if (t < JP_BWT_UNITS) {
+		const u8* p = in + len + 4 * t;
+		u32 v = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+		i32 r = (i32)v;
+		if (r < 1 || r > nlen) { dev_fail(err, DE_BAD_INDEX); r = 1; }
+		row[t] = r;
+	}
+	if (t == JP_BWT_UNITS) row[t] = 0;
+	__syncthreads();
+	if (t < N_ANCHOR) {
+		const i32 mine = row[t];
+		int rank = 0;
+		for (int j = 0; j < N_ANCHOR; j++) {
+			const i32 o = row[j];
+			if (o < mine || (o == mine && j < t)) rank++;
+			if (o == mine && j != t) dev_fail(err, DE_BAD_INDEX);   // anchors must be distinct rows
+		}
+		meta->anchor_row[t] = mine;
+		meta->sorted_row[rank] = mine;
+		meta->sorted_id[rank] = t;
+		if (t == 0) meta->idx = mine;
+	}
+	for (int i = t; i < len - nlen; i += blockDim.x) out[nlen + i] = in[nlen + i];   // bwt.cpp:82-83
+}
+
+// ---- byte histogram per 64 KiB tile (bwt.cpp:141-167) --------------------------------------------
+// BWT output is run-heavy, so same-address shared atomics would serialise; each thread folds the runs
+// inside its own 16 bytes before touching the per-warp histogram.
+__global__ void __launch_bounds__(INV_THREADS) k_inv_hist(const u8* __restrict__ bwt, i32 n, u32* __restrict__ tile_hist)
+{
+	__shared__ u32 h[INV_WARPS][256];
+	const int t = threadIdx.x, w = t >> 5;
+	for (int i = t; i < INV_WARPS * 256; i += INV_THREADS) (&h[0][0])[i] = 0;
+	__syncthreads();
+	const i64 base = (i64)blockIdx.x * INV_TILE;
+	const i64 end = min((i64)n, base + INV_TILE);
+	u32* hw = h[w];
+	for (i64 p = base + (i64)t * 16; p < end; p += INV_THREADS * 16) {
+		if (p + 16 <= end) {
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(bwt + p));
+			const u32 wd[4] = {q.x, q.y, q.z, q.w};
+			u32 cur = wd[0] & 255, run = 0;
+			#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				const u32 c = (wd[k >> 2] >> ((k & 3) * 8)) & 255;
+				if (c != cur) { atomicAdd(&hw[cur], run); cur = c; run = 0; }
+				run++;
+			}
+			atomicAdd(&hw[cur], run);
+		} else {
+			for (i64 q = p; q < end; q++) atomicAdd(&hw[bwt[q]], 1u);
+		}
+	}
+	__syncthreads();
+	u32 s = 0;
+	#pragma unroll
+	for (int k = 0; k < INV_WARPS; k++) s += h[k][t];
+	tile_hist[(size_t)blockIdx.x * 256 + t] = s;
+}
+
+// ---- per-symbol exclusive scan down the tiles; block b owns symbol b ------------------------------
+__global__ void __launch_bounds__(256) k_inv_scan_tiles(u32* __restrict__ tile_hist, int tiles, u32* __restrict__ bin_total)
+{
+	__shared__ u32 ws[32];
+	const int b = blockIdx.x, t = threadIdx.x;
+	const int per = (tiles + 255) / 256;
+	const int lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	u32 s = 0;
+	for (int k = lo; k < hi; k++) s += tile_hist[(size_t)k * 256 + b];
+	u32 total;
+	u32 inc = block_incl_sum(s, ws, &total);
+	u32 run = inc - s;
+	for (int k = lo; k < hi; k++) {
+		const size_t a = (size_t)k * 256 + b;
+		const u32 v = tile_hist[a];
+		tile_hist[a] = run;
+		run += v;
+	}
+	if (t == 0) bin_total[b] = total;
+}
+
+// ---- C table: exclusive prefix sum of the 256 totals (bwt.cpp:168-169) ----------------------------
+__global__ void __launch_bounds__(256) k_inv_ctable(const u32* __restrict__ bin_total, InvMeta* __restrict__ meta, i32 n)
+{
+	__shared__ u32 ws[32];
+	const int t = threadIdx.x;
+	const u32 v = bin_total[t];
+	u32 total;
+	const u32 inc = block_incl_sum(v, ws, &total);
+	meta->ctable[t] = (i32)(inc - v);
+	if (t == 255) meta->ctable[256] = (i32)inc;   // == n
+	(void)n;
+}
+
+// ---- LF/rank table build --------------------------------------------------------------------------
+// One block per 64 KiB tile, 4 KiB per iteration. Each warp owns 512 consecutive bytes, read as four
+// coalesced 128 B rows of 32-bit words and re-distributed by shuffle so that lane l handles byte
+// 32*k + l of the row (text order == lane order). Equal bytes inside a warp step are ranked with
+// match.any; running per-warp counters live in shared memory; LF values leave as 128 B coalesced rows.
+__global__ void __launch_bounds__(INV_THREADS) k_inv_lf(const u8* __restrict__ bwt, i32 n,
+                                                        const u32* __restrict__ tile_excl, const InvMeta* __restrict__ meta,
+                                                        u32* __restrict__ lf, int log2m)
+{
+	__shared__ u32 wcnt[INV_WARPS][256];
+	__shared__ u32 basec[256];
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	const u32 lt = lanemask_lt();
+	const u32 mmask = (1u << log2m) - 1;
+	basec[t] = 1u + (u32)meta->ctable[t] + tile_excl[(size_t)blockIdx.x * 256 + t];
+	const i64 tile_base = (i64)blockIdx.x * INV_TILE;
+	const i64 tile_end = min((i64)n, tile_base + INV_TILE);
+
+	for (i64 cb = tile_base; cb < tile_end; cb += INV_CHUNK) {
+		for (int i = t; i < INV_WARPS * 256; i += INV_THREADS) (&wcnt[0][0])[i] = 0;
+		__syncthreads();
+
+		const i64 seg = cb + (i64)w * 512;
+		u32 word[4];
+		#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			const i64 p = seg + r * 128 + lane * 4;
+			u32 v = 0;
+			if (p + 4 <= n) v = __ldg(reinterpret_cast<const u32*>(bwt + p));
+			else { for (int b = 0; b < 4; b++) if (p + b < n) v |= (u32)bwt[p + b] << (8 * b); }
+			word[r] = v;
+		}
+		u32 lrank[16];
+		u32* mycnt = wcnt[w];
+		#pragma unroll
+		for (int it = 0; it < 16; it++) {
+			const int r = it >> 2, k = it & 3;
+			const u32 src = __shfl_sync(0xffffffffu, word[r], 8 * k + (lane >> 2));
+			const i64 gp = seg + r * 128 + k * 32 + lane;
+			const bool valid = gp < n;
+			const u32 c = valid ? ((src >> (8 * (lane & 3))) & 255u) : 256u;
+			const u32 peers = __match_any_sync(0xffffffffu, c);
+			const u32 below = __popc(peers & lt);
+			u32 before = 0;
+			if (below == 0 && valid) { before = mycnt[c]; mycnt[c] = before + __popc(peers); }
+			before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+			lrank[it] = before + below;
+			__syncwarp();
+		}
+		__syncthreads();
+		{   // exclusive scan across the warps of this chunk, folded into the running per-symbol base
+			u32 run = basec[t];
+			#pragma unroll
+			for (int k = 0; k < INV_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+			basec[t] = run;
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int it = 0; it < 16; it++) {
+			const int r = it >> 2, k = it & 3;
+			const u32 src = __shfl_sync(0xffffffffu, word[r], 8 * k + (lane >> 2));
+			const i64 gp = seg + r * 128 + k * 32 + lane;
+			if (gp < n) {
+				const u32 c = (src >> (8 * (lane & 3))) & 255u;
+				u32 v = mycnt[c] + lrank[it];
+				const u32 gi = (u32)gp;
+				if ((gi & mmask) == (mix32(gi >> log2m) & mmask)) v |= LF_MARK;
+				lf[gp] = v;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+__device__ __forceinline__ i32 row_to_byte(i32 row, i32 idx) { return row - (row > idx ? 1 : 0); }
+
+// ---- mark the anchors (stored indices 1..119 and row 0) -------------------------------------------
+__global__ void k_inv_mark_anchors(const InvMeta* __restrict__ meta, u32* __restrict__ lf, i32 n)
+{
+	const int k = threadIdx.x;
+	if (k >= 1 && k < N_ANCHOR) {
+		const i32 idx = meta->idx;
+		i32 i = row_to_byte(meta->anchor_row[k], idx);
+		if (i < 0) i = 0;
+		if (i >= n) i = n - 1;          // only reachable with indices already flagged as bad
+		atomicOr(&lf[i], LF_MARK);
+	}
+}
+
+// ---- walkers ---------------------------------------------------------------------------------------
+struct AnchorTable {
+	i32 row[N_ANCHOR];
+	i32 id[N_ANCHOR];
+};
+
+__device__ __forceinline__ void load_anchor_table(AnchorTable& a, const InvMeta* meta)
+{
+	for (int i = threadIdx.x; i < N_ANCHOR; i += blockDim.x) { a.row[i] = meta->sorted_row[i]; a.id[i] = meta->sorted_id[i]; }
+}
+
+// node id of the marked row `row` (byte index bi): an anchor if it is one, else the window's splitter
+__device__ __forceinline__ u32 node_of(const AnchorTable& a, i32 row, i32 bi, int log2m, u32 S)
+{
+	int lo = 0, hi = N_ANCHOR;          // first position with a.row[pos] >= row
+	while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.row[mid] < row) lo = mid + 1; else hi = mid; }
+	if (lo < N_ANCHOR && a.row[lo] == row) return S + (u32)a.id[lo];
+	return (u32)bi >> log2m;
+}
+
+// start row (as a byte index) of node `id`, or -1 when the node does not exist
+__device__ __forceinline__ i32 node_start(u32 id, u32 S, i32 n, int log2m, const InvMeta* meta, i32 idx)
+{
+	if (id < S) {
+		const u32 m1 = (1u << log2m) - 1;
+		const u32 bi = (id << log2m) + (mix32(id) & m1);
+		return bi < (u32)n ? (i32)bi : -1;
+	}
+	const u32 k = id - S;
+	if (k == 0) return -1;              // anchor 0 is the terminal (text position 0): nothing lies to its left
+	return row_to_byte(meta->anchor_row[k], idx);
+}
+
+__device__ __forceinline__ u64 pack_rec(u32 next, u32 dist) { return ((u64)next << 32) | dist; }
+
+// Pass 1: per sub-chain (next node, length). Lanes refill independently from a global ticket counter so a
+// warp is not held hostage by its longest (geometrically distributed) sub-chain.
+__global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
+                                                              i32 n, int log2m, u32 S, u64* __restrict__ rec,
+                                                              u32* __restrict__ ticket)
+{
+	__shared__ AnchorTable anchors;
+	load_anchor_table(anchors, meta);
+	__syncthreads();
+	const i32 idx = meta->idx;
+	const u32 nodes = S + N_ANCHOR;
+	const u32 lane = lane_id(), lt = lanemask_lt();
+	u32 id = REC_INVALID, v = 0, len = 0;
+	bool done = false;
+	for (;;) {
+		const bool need = !done && id == REC_INVALID;
+		const u32 nm = __ballot_sync(0xffffffffu, need);
+		if (nm) {
+			const int leader = __ffs(nm) - 1;
+			u32 base = 0;
+			if ((int)lane == leader) base = atomicAdd(ticket, (u32)__popc(nm));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (need) {
+				const u32 my = base + __popc(nm & lt);
+				if (my >= nodes) done = true;
+				else {
+					const i32 bi = node_start(my, S, n, log2m, meta, idx);
+					if (bi < 0) rec[my] = pack_rec(REC_INVALID, 0);
+					else { id = my; len = 0; v = lf[bi]; }
+				}
+			}
+		}
+		if (__ballot_sync(0xffffffffu, !done) == 0) break;
+		if (id != REC_INVALID) {
+			const i32 r = (i32)(v & LF_MASK);
+			len++;
+			if (r == idx) { rec[id] = pack_rec(S, len); id = REC_INVALID; }
+			else {
+				const i32 bi = row_to_byte(r, idx);
+				v = lf[bi];
+				if (v & LF_MARK) { rec[id] = pack_rec(node_of(anchors, r, bi, log2m, S), len); id = REC_INVALID; }
+			}
+		}
+	}
+}
+
+// Ranking: asynchronous pointer jumping. A record (next, dist) always means "dist bytes to the left of my
+// start lies the start of `next`"; replacing it by (next.next, dist + next.dist) keeps that true whichever
+// version of next's record was read, so no double buffering or rounds are needed: 8-byte loads/stores are
+// single transactions. Anchors (ids >= S) absorb.
+__global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err)
+{
+	const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 nodes = S + N_ANCHOR;
+	if (id >= nodes) return;
+	volatile u64* vrec = rec;
+	u64 r = vrec[id];
+	u32 nxt = (u32)(r >> 32), dist = (u32)r;
+	if (nxt == REC_INVALID) return;
+	int hops = 0;
+	while (nxt < S) {
+		const u64 o = vrec[nxt];
+		nxt = (u32)(o >> 32);
+		dist += (u32)o;
+		if (nxt == REC_INVALID || ++hops > RANK_HOP_CAP) { dev_fail(err, DE_RANK_LOOP); nxt = S; dist = 0; break; }
+		vrec[id] = pack_rec(nxt, dist);
+	}
+	vrec[id] = pack_rec(nxt, dist);
+	if (id > S) {   // decode unit k-1 runs from anchor k down to anchor k-1 and is exactly `step` long
+		if (nxt != id - 1 || dist != (u32)step) dev_fail(err, DE_CHAIN_LEN);
+	}
+}
+
+__device__ __forceinline__ u32 symbol_of_row(const i32* __restrict__ C, i32 row)
+{
+	const i32 x = row - 1;              // F[row] = c  <=>  C[c] <= row-1 < C[c+1]
+	u32 lo = 0;
+	#pragma unroll
+	for (u32 s = 128; s > 0; s >>= 1) if (C[lo + s] <= x) lo += s;
+	return lo;
+}
+
+// Pass 2: the same walk, now emitting. Bytes are produced right-to-left and packed into a 32-bit
+// accumulator; full words go out as aligned 32-bit stores, the (shared) partial words at either end of a
+// sub-chain as byte stores.
+__global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
+                                                               i32 n, i32 step, int log2m, u32 S, const u64* __restrict__ rec,
+                                                               u32* __restrict__ ticket, u8* __restrict__ out,
+                                                               int* __restrict__ err)
+{
+	__shared__ i32 C[257];
+	for (int i = threadIdx.x; i < 257; i += blockDim.x) C[i] = meta->ctable[i];
+	__syncthreads();
+	const i32 idx = meta->idx;
+	const u32 nodes = S + N_ANCHOR;
+	const u32 lane = lane_id(), lt = lanemask_lt();
+	u32 id = REC_INVALID, v = 0, acc = 0;
+	i32 pos = 0, pos_end = 0;
+	bool done = false;
+	for (;;) {
+		const bool need = !done && id == REC_INVALID;
+		const u32 nm = __ballot_sync(0xffffffffu, need);
+		if (nm) {
+			const int leader = __ffs(nm) - 1;
+			u32 base = 0;
+			if ((int)lane == leader) base = atomicAdd(ticket, (u32)__popc(nm));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (need) {
+				const u32 my = base + __popc(nm & lt);
+				if (my >= nodes) done = true;
+				else {
+					const u64 r = rec[my];
+					const u32 nxt = (u32)(r >> 32);
+					const i32 bi = (nxt == REC_INVALID) ? -1 : node_start(my, S, n, log2m, meta, idx);
+					if (bi >= 0) {
+						const i64 pe = (i64)(nxt - S) * step + (u32)r;
+						if (nxt < S || pe > n || pe <= 0) dev_fail(err, DE_CHAIN_RANGE);
+						else { id = my; pos = pos_end = (i32)pe; acc = 0; v = lf[bi]; }
+					}
+				}
+			}
+		}
+		if (__ballot_sync(0xffffffffu, !done) == 0) break;
+		if (id != REC_INVALID) {
+			const i32 r = (i32)(v & LF_MASK);
+			bool stop = (r == idx);
+			if (!stop) {
+				v = lf[row_to_byte(r, idx)];       // next gather goes out before the symbol search below
+				stop = (v & LF_MARK) != 0;
+			}
+			const u32 c = symbol_of_row(C, r);
+			if (pos <= 0) { dev_fail(err, DE_CHAIN_RANGE); stop = true; }
+			else {
+				pos--;
+				acc |= c << ((pos & 3) * 8);
+				if ((pos & 3) == 0) {
+					if (pos + 4 <= pos_end) *reinterpret_cast<u32*>(out + pos) = acc;
+					else for (i32 q = pos; q < pos_end; q++) out[q] = (u8)(acc >> ((q & 3) * 8));
+					acc = 0;
+				}
+			}
+			if (stop) {
+				if (pos & 3) {
+					const i32 top = min(pos_end, (pos & ~3) + 4);
+					for (i32 q = pos; q < top; q++) out[q] = (u8)(acc >> ((q & 3) * 8));
+				}
+				id = REC_INVALID;
+			}
+		}
+	}
+}
+
+// ---- host driver -----------------------------------------------------------------------------------
+static int pick_log2m(i32 nlen)
+{
+	int lg = 6;
+	if (const char* e = getenv("JP_BWT_INV_LOG2M")) { int v = atoi(e); if (v >= 2 && v <= 12) return v; }
+	// aim for >= 2^19 sub-chains, spacing between 8 and 64 rows
+	while (lg > 3 && ((i64)nlen >> lg) < (1 << 19)) lg--;
+	return lg;
+}
+
+static int walker_blocks(Ctx& c, const void* kernel)
+{
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, INV_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+	return c.sm_count * per_sm;
+}
+
+struct InvBuffers {
+	u32* lf; u32* tile_hist; u32* bin_total; InvMeta* meta; u64* rec; u32* ticket; int* err;
+	int tiles; int log2m; u32 S;
+};
+
+static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b)
+{
+	b.tiles = (int)(((i64)nlen + INV_TILE - 1) / INV_TILE);
+	b.log2m = pick_log2m(nlen);
+	b.S = (u32)(((i64)nlen + (1 << b.log2m) - 1) >> b.log2m);
+	const size_t nodes = (size_t)b.S + N_ANCHOR;
+	size_t total = Arena::align((size_t)nlen * 4) + Arena::align((size_t)b.tiles * 256 * 4) + Arena::align(256 * 4) +
+	               Arena::align(sizeof(InvMeta)) + Arena::align(nodes * 8) + Arena::align(64) + Arena::align(64);
+	JP_TRY(arena_reserve(c, total));
+	b.lf = arena_take<u32>(c, (size_t)nlen);
+	b.tile_hist = arena_take<u32>(c, (size_t)b.tiles * 256);
+	b.bin_total = arena_take<u32>(c, 256);
+	b.meta = arena_take<InvMeta>(c, 1);
+	b.rec = arena_take<u64>(c, nodes);
+	b.ticket = arena_take<u32>(c, 16);
+	b.err = arena_take<int>(c, 16);
+	return JP_OK;
+}
+
+static int inv_build_table(Ctx& c, const u8* d_in, i32 len, i32 nlen, u8* d_out, InvBuffers& b, cudaStream_t s)
+{
+	JP_CUDA(cudaMemsetAsync(b.ticket, 0, 64, s));
+	JP_CUDA(cudaMemsetAsync(b.err, 0, 64, s));
+	k_inv_prepare<<<1, 128, 0, s>>>(d_in, len, nlen, d_out, b.meta, b.err); JP_LAUNCH(c);
+	k_inv_hist<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist); JP_LAUNCH(c);
+	k_inv_scan_tiles<<<256, 256, 0, s>>>(b.tile_hist, b.tiles, b.bin_total); JP_LAUNCH(c);
+	k_inv_ctable<<<1, 256, 0, s>>>(b.bin_total, b.meta, nlen); JP_LAUNCH(c);
+	JP_KCHECK();
+	return JP_OK;
+}
+
+int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st)
+{
+	const i32 len = len_with_trailer - JP_BWT_TRAILER_BYTES;            // bwt.cpp:77
+	if (len < 0) return JP_ERR_ARG;
+	const i32 nlen = len - len % JP_BWT_UNITS;                          // bwt.cpp:80-81
+	st->direction = 1; st->len = len; st->nlen = nlen; st->device = c.device;
+	JP_CUDA(cudaEventRecord(c.ev[0], s));
+	if (nlen == 0) {                                                    // bwt.cpp:85: nothing but the raw tail
+		if (len > 0) JP_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)len, cudaMemcpyDeviceToDevice, s));
+		JP_CUDA(cudaEventRecord(c.ev[1], s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[1]));
+		return JP_OK;
+	}
+	const i32 step = nlen / JP_BWT_UNITS;                               // bwt.cpp:176 with N_Units = 120
+	InvBuffers b;
+	JP_TRY(inv_alloc(c, nlen, b));
+	JP_TRY(inv_build_table(c, d_in, len, nlen, d_out, b, s));
+	JP_CUDA(cudaEventRecord(c.ev[1], s));
+	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
+	k_inv_mark_anchors<<<1, 128, 0, s>>>(b.meta, b.lf, nlen); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[2], s));
+	const u32 nodes = b.S + N_ANCHOR;
+	const int wb1 = walker_blocks(c, (const void*)k_inv_walk_len);
+	k_inv_walk_len<<<wb1, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[3], s));
+	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[4], s));
+	const int wb2 = walker_blocks(c, (const void*)k_inv_walk_emit);
+	k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaEventRecord(c.ev[5], s));
+	JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	for (int i = 0; i < 5; i++) JP_CUDA(cudaEventElapsedTime(&st->ms_phase[i], c.ev[i], c.ev[i + 1]));
+	JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[5]));
+	st->subchains = (i32)nodes;
+	st->subchain_spacing = 1 << b.log2m;
+	st->device_bytes = c.arena.high;
+	st->random_sectors = 2ull * (u64)nlen;
+	return map_dev_err(c.h_small[0]);
+}
+
+// ---- test hook: the LF table itself -----------------------------------------------------------------
+__global__ void k_strip_marks(u32* lf, i32 n)
+{
+	const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) lf[i] &= LF_MASK;
+}
+
+int debug_lf(Ctx& c, const u8* h_in, i32 nlen, i32* h_lf, i32* h_ctable)
+{
+	if (nlen <= 0) return JP_ERR_ARG;
+	cudaStream_t s = c.own_stream;
+	InvBuffers b;
+	c.arena.reset();
+	const size_t extra = Arena::align((size_t)nlen + JP_BWT_TRAILER_BYTES + 16) + Arena::align((size_t)nlen + 16);
+	JP_TRY(arena_reserve(c, extra + (size_t)nlen * 6 + (4 << 20)));
+	u8* d_in = arena_take<u8>(c, (size_t)nlen + JP_BWT_TRAILER_BYTES + 16);
+	u8* d_out = arena_take<u8>(c, (size_t)nlen + 16);
+	JP_TRY(inv_alloc(c, nlen, b));
+	JP_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nlen + JP_BWT_TRAILER_BYTES, s));
+	JP_CUDA(cudaMemcpyAsync(d_in, h_in, (size_t)nlen, cudaMemcpyHostToDevice, s));
+	// a syntactically valid trailer (all distinct, in range) so prepare does not flag it
+	{
+		i32 fake[JP_BWT_UNITS];
+		for (int k = 0; k < JP_BWT_UNITS; k++) fake[k] = 1 + (i32)(((i64)k * nlen) / JP_BWT_UNITS);
+		JP_CUDA(cudaMemcpyAsync(d_in + nlen, fake, sizeof(fake), cudaMemcpyHostToDevice, s));
+		JP_CUDA(cudaStreamSynchronize(s));
+	}
+	JP_TRY(inv_build_table(c, d_in, nlen, nlen, d_out, b, s));
+	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
+	k_strip_marks<<<(nlen + 255) / 256, 256, 0, s>>>(b.lf, nlen); JP_LAUNCH(c);
+	JP_KCHECK();
+	JP_CUDA(cudaMemcpyAsync(h_lf, b.lf, (size_t)nlen * 4, cudaMemcpyDeviceToHost, s));
+	InvMeta hm;
+	JP_CUDA(cudaMemcpyAsync(&hm, b.meta, sizeof(InvMeta), cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	for (int i = 0; i < 257; i++) h_ctable[i] = hm.ctable[i];
+	return JP_OK;
+}
+
+// ---- micro-benchmark: random 4-byte gathers (the roofline denominator) -----------------
+__global__ void k_fill_perm(u32* tab, u32 n_words)
+{
+	// successor table = the bijection x -> (a*x + c) mod 2^k (a odd): walkers never merge, so no step is
+	// served from a line another walker just pulled in. n_words is a power of two.
+	const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_words) tab[i] = ((u32)i * 0x9E3779B1u + 0x7F4A7C15u) & (n_words - 1);
+}
+__global__ void __launch_bounds__(256) k_gather_dep(const u32* __restrict__ tab, u32 n_words, int steps, u32* __restrict__ sink)
+{
+	const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 p = (u32)(((u64)mix32(gid + 1) * n_words) >> 32);
+	for (int i = 0; i < steps; i++) p = tab[p];
+	if (p == 0xffffffffu) sink[0] = p;
+}
+__global__ void __launch_bounds__(256) k_gather_indep(const u32* __restrict__ tab, u32 n_words, int steps, u32* __restrict__ sink)
+{
+	const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 acc = 0, x = gid * 0x9E3779B1u + 7u;
+	#pragma unroll 4
+	for (int i = 0; i < steps; i++) { x = x * 1664525u + 1013904223u; acc += tab[(u32)(((u64)mix32(x) * n_words) >> 32)]; }
+	if (acc == 0x12345678u) sink[0] = acc;
+}
+
+double debug_gather_rate(Ctx& c, u64 table_bytes, i32 chains, i32 steps, int dependent)
+{
+	cudaStream_t s = c.own_stream;
+	if (table_bytes < 1024 || table_bytes > (8ull << 30) || chains <= 0 || steps <= 0) return JP_ERR_ARG;
+	u32 n_words = 1;
+	while ((u64)n_words * 8 <= table_bytes) n_words <<= 1;   // largest power of two with 4*n_words <= table_bytes
+	c.arena.reset();
+	if (arena_reserve(c, Arena::align((size_t)n_words * 4) + 4096) != JP_OK) return JP_ERR_OOM;
+	u32* tab = arena_take<u32>(c, n_words);
+	u32* sink = arena_take<u32>(c, 16);
+	k_fill_perm<<<(n_words + 255) / 256, 256, 0, s>>>(tab, n_words);
+	const int blocks = (chains + 255) / 256;
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; rep++) {
+		cudaEventRecord(c.ev[0], s);
+		if (dependent) k_gather_dep<<<blocks, 256, 0, s>>>(tab, n_words, steps, sink);
+		else k_gather_indep<<<blocks, 256, 0, s>>>(tab, n_words, steps, sink);
+		cudaEventRecord(c.ev[1], s);
+		if (cudaStreamSynchronize(s) != cudaSuccess) return JP_ERR_CUDA;
+		float ms = 0; cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+		if (rep > 0 && ms < best) best = ms;
+	}
+	return (double)blocks * 256.0 * (double)steps / ((double)best * 1e-3);
+}
+
+} // namespace jp

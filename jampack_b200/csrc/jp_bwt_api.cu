@@ -1,0 +1,285 @@
+// jp_bwt_api.cu -- the C-ABI of include/jp_bwt.h: context pool (device, stream, workspace), block
+// sharding over devices, host<->device staging, error and stats plumbing. No kernels live here.
+#include "bwt_internal.cuh"
+
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace jp {
+
+static thread_local char          t_detail[512] = "";
+static thread_local jp_bwt_stats  t_stats = {};
+
+void set_error_detail(const char* fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(t_detail, sizeof(t_detail), fmt, ap);
+	va_end(ap);
+}
+
+int map_dev_err(int de)
+{
+	switch (de) {
+	case DE_NONE: return JP_OK;
+	case DE_BAD_INDEX: set_error_detail("stored primary index outside [1, nlen] or duplicated"); return JP_ERR_BAD_INDEX;
+	case DE_CHAIN_LEN: set_error_detail("a decode unit's chain is not nlen/120 long"); return JP_ERR_CORRUPT;
+	case DE_CHAIN_RANGE: set_error_detail("a sub-chain leaves its block"); return JP_ERR_CORRUPT;
+	case DE_RANK_LOOP: set_error_detail("sub-chain ranking found a cycle"); return JP_ERR_CORRUPT;
+	case DE_FWD_RANGE: set_error_detail("forward: rank lookup beyond the end of the block"); return JP_ERR_INTERNAL;
+	case DE_FWD_ROUNDS: set_error_detail("forward: prefix doubling did not converge"); return JP_ERR_INTERNAL;
+	default: set_error_detail("device error flag %d", de); return JP_ERR_INTERNAL;
+	}
+}
+
+int arena_reserve(Ctx& c, size_t total)
+{
+	if (c.arena.cap - c.arena.off >= total) return JP_OK;
+	if (c.arena.off != 0) { set_error_detail("arena: %zu more bytes wanted with %zu live", total, c.arena.off); return JP_ERR_INTERNAL; }
+	if (c.arena.base) { JP_CUDA(cudaFree(c.arena.base)); c.arena.base = nullptr; c.arena.cap = 0; }
+	const size_t want = (total + (64u << 20) - 1) & ~(size_t)((64u << 20) - 1);
+	JP_CUDA(cudaMalloc(&c.arena.base, want));
+	c.arena.cap = want;
+	return JP_OK;
+}
+
+// ---- context pool -----------------------------------------------------------------------------------
+static const int MAX_CTX_PER_DEVICE = 4;
+
+struct Pool {
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<int> devices;
+	bool devices_ready = false;
+	std::vector<std::unique_ptr<Ctx>> ctxs;
+	unsigned rr = 0;
+};
+static Pool g_pool;
+
+static int visible_devices()
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+static int init_devices_locked()
+{
+	if (g_pool.devices_ready) return g_pool.devices.empty() ? JP_ERR_NO_DEVICE : JP_OK;
+	const int n = visible_devices();
+	g_pool.devices.clear();
+	if (const char* e = getenv("JP_BWT_DEVICES")) {
+		const char* p = e;
+		while (*p) {
+			char* end; long v = strtol(p, &end, 10);
+			if (end == p) break;
+			if (v >= 0 && v < n) g_pool.devices.push_back((int)v);
+			p = (*end == ',') ? end + 1 : end;
+		}
+	}
+	if (g_pool.devices.empty()) for (int i = 0; i < n; i++) g_pool.devices.push_back(i);
+	g_pool.devices_ready = true;
+	if (g_pool.devices.empty()) { set_error_detail("no CUDA device visible; this stage has no CPU path"); return JP_ERR_NO_DEVICE; }
+	return JP_OK;
+}
+
+static int create_ctx(int device, Ctx** out)
+{
+	std::unique_ptr<Ctx> c(new Ctx());
+	c->device = device;
+	JP_CUDA(cudaSetDevice(device));
+	JP_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	JP_CUDA(cudaMallocHost(&c->h_small, 64 * sizeof(int)));
+	for (auto& e : c->ev) JP_CUDA(cudaEventCreate(&e));
+	JP_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+	c->busy = true;
+	*out = c.get();
+	g_pool.ctxs.push_back(std::move(c));
+	return JP_OK;
+}
+
+// device < 0: next device in round-robin order (whole blocks are the unit of sharding)
+static int acquire(int device, Ctx** out)
+{
+	std::unique_lock<std::mutex> lk(g_pool.mu);
+	JP_TRY(init_devices_locked());
+	if (device < 0) device = g_pool.devices[g_pool.rr++ % g_pool.devices.size()];
+	else if (device >= visible_devices()) { set_error_detail("device %d not visible", device); return JP_ERR_NO_DEVICE; }
+	for (;;) {
+		int have = 0;
+		for (auto& c : g_pool.ctxs) {
+			if (c->device != device) continue;
+			have++;
+			if (!c->busy) { c->busy = true; *out = c.get(); lk.unlock(); JP_CUDA(cudaSetDevice(device)); return JP_OK; }
+		}
+		if (have < MAX_CTX_PER_DEVICE) return create_ctx(device, out);
+		g_pool.cv.wait(lk);
+	}
+}
+
+static void release(Ctx* c)
+{
+	{ std::lock_guard<std::mutex> lk(g_pool.mu); c->busy = false; }
+	g_pool.cv.notify_all();
+}
+
+struct CtxGuard {
+	Ctx* c = nullptr;
+	~CtxGuard() { if (c) release(c); }
+};
+
+static int ensure_io(Ctx& c, size_t bytes)
+{
+	bytes = Arena::align(bytes + 64);
+	if (c.d_io_cap >= bytes) return JP_OK;
+	if (c.d_in) { JP_CUDA(cudaFree(c.d_in)); c.d_in = nullptr; }
+	if (c.d_out) { JP_CUDA(cudaFree(c.d_out)); c.d_out = nullptr; }
+	c.d_io_cap = 0;
+	JP_CUDA(cudaMalloc(&c.d_in, bytes));
+	JP_CUDA(cudaMalloc(&c.d_out, bytes));
+	c.d_io_cap = bytes;
+	return JP_OK;
+}
+
+static void begin_call(Ctx& c)
+{
+	c.launches = 0;
+	c.arena.reset();
+	c.arena.high = 0;
+	memset(&t_stats, 0, sizeof(t_stats));
+	t_detail[0] = 0;
+}
+
+static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_len)
+{
+	if (!in || !out || !out_len || in_len < 0) { set_error_detail("null pointer or negative length"); return JP_ERR_ARG; }
+	if (direction == 1 && in_len < JP_BWT_TRAILER_BYTES) { set_error_detail("inverse input shorter than its trailer"); return JP_ERR_ARG; }
+	const i32 len = direction == 0 ? in_len : in_len - JP_BWT_TRAILER_BYTES;
+	if ((i64)len > (i64)JP_BWT_MAX_LEN * 105 / 100) { set_error_detail("block longer than 1.05 * MAX_BLOCKSIZE"); return JP_ERR_ARG; }
+	const i32 nlen = len - len % JP_BWT_UNITS;
+	*out_len = direction == 0 ? len + JP_BWT_TRAILER_BYTES : len;          // bwt.cpp:27 / :78
+	CtxGuard g;
+	JP_TRY(acquire(-1, &g.c));
+	Ctx& c = *g.c;
+	begin_call(c);
+	cudaStream_t s = c.own_stream;
+	JP_TRY(ensure_io(c, (size_t)len + JP_BWT_TRAILER_BYTES));
+	const size_t in_bytes = (size_t)in_len;
+	// forward: the trailer exists only when something was transformed (bwt.cpp:35)
+	const size_t out_bytes = direction == 0 ? (size_t)len + (nlen > 0 ? JP_BWT_TRAILER_BYTES : 0) : (size_t)len;
+	JP_CUDA(cudaEventRecord(c.ev[8], s));
+	if (in_bytes) JP_CUDA(cudaMemcpyAsync(c.d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
+	JP_CUDA(cudaEventRecord(c.ev[9], s));
+	int rc = direction == 0 ? forward_device(c, c.d_in, len, c.d_out, s, &t_stats)
+	                        : inverse_device(c, c.d_in, in_len, c.d_out, s, &t_stats);
+	if (rc != JP_OK) return rc;
+	JP_CUDA(cudaEventRecord(c.ev[10], s));
+	if (out_bytes) JP_CUDA(cudaMemcpyAsync(out, c.d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaEventRecord(c.ev[11], s));
+	JP_CUDA(cudaStreamSynchronize(s));
+	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_h2d, c.ev[8], c.ev[9]));
+	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
+	t_stats.kernel_launches = c.launches;
+	t_stats.device_bytes = c.arena.high;
+	return JP_OK;
+}
+
+static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int device, void* stream)
+{
+	if (!d_in || !d_out || in_len < 0 || device < 0) { set_error_detail("null pointer, negative length or device"); return JP_ERR_ARG; }
+	if (direction == 1 && in_len < JP_BWT_TRAILER_BYTES) { set_error_detail("inverse input shorter than its trailer"); return JP_ERR_ARG; }
+	if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) { set_error_detail("device blocks must be 16-byte aligned"); return JP_ERR_ARG; }
+	CtxGuard g;
+	JP_TRY(acquire(device, &g.c));
+	Ctx& c = *g.c;
+	begin_call(c);
+	cudaStream_t s = stream ? (cudaStream_t)stream : c.own_stream;
+	int rc = direction == 0 ? forward_device(c, d_in, in_len, d_out, s, &t_stats)
+	                        : inverse_device(c, d_in, in_len, d_out, s, &t_stats);
+	t_stats.kernel_launches = c.launches;
+	t_stats.device_bytes = c.arena.high;
+	return rc;
+}
+
+} // namespace jp
+
+using namespace jp;
+
+extern "C" {
+
+int jp_bwt_forward(const uint8_t* in, int32_t len, uint8_t* out, int32_t* out_len) { return host_call(0, in, len, out, out_len); }
+int jp_bwt_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, int32_t* out_len) { return host_call(1, in, len_with_trailer, out, out_len); }
+int jp_bwt_forward_device(const uint8_t* d_in, int32_t len, uint8_t* d_out, int device, void* stream) { return device_call(0, d_in, len, d_out, device, stream); }
+int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream) { return device_call(1, d_in, len_with_trailer, d_out, device, stream); }
+
+int jp_bwt_set_devices(const int* ids, int n)
+{
+	std::lock_guard<std::mutex> lk(g_pool.mu);
+	if (n <= 0 || !ids) { g_pool.devices_ready = false; return init_devices_locked(); }
+	const int vis = visible_devices();
+	if (vis == 0) { set_error_detail("no CUDA device visible; this stage has no CPU path"); return JP_ERR_NO_DEVICE; }
+	std::vector<int> d;
+	for (int i = 0; i < n; i++) { if (ids[i] < 0 || ids[i] >= vis) { set_error_detail("device %d not visible", ids[i]); return JP_ERR_ARG; } d.push_back(ids[i]); }
+	g_pool.devices = d;
+	g_pool.devices_ready = true;
+	g_pool.rr = 0;
+	return JP_OK;
+}
+
+int jp_bwt_device_count(void)
+{
+	std::lock_guard<std::mutex> lk(g_pool.mu);
+	if (init_devices_locked() != JP_OK) return 0;
+	return (int)g_pool.devices.size();
+}
+
+void* jp_bwt_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+void jp_bwt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int jp_bwt_last_stats(jp_bwt_stats* out) { if (!out) return JP_ERR_ARG; *out = t_stats; return JP_OK; }
+
+const char* jp_bwt_strerror(int rc)
+{
+	switch (rc) {
+	case JP_OK: return "ok";
+	case JP_ERR_ARG: return "Bwt :: invalid argument";
+	case JP_ERR_NO_DEVICE: return "Bwt :: no CUDA device (this stage has no CPU path)";
+	case JP_ERR_CUDA: return "Bwt :: CUDA error";
+	case JP_ERR_OOM: return "Bwt :: out of device or pinned memory";
+	case JP_ERR_BAD_INDEX: return "Bwt :: stored primary index out of range";
+	case JP_ERR_CORRUPT: return "Bwt :: inconsistent BWT block";
+	case JP_ERR_INTERNAL: return "Bwt :: internal invariant failed";
+	default: return "Bwt :: unknown error";
+	}
+}
+const char* jp_bwt_last_error_detail(void) { return t_detail; }
+const char* jp_bwt_version(void) { return "jampack-bwt-b200 0.1 (sm_100a)"; }
+
+int jp_bwt_debug_lf(const uint8_t* in, int32_t nlen, int32_t* lf, int32_t* ctable)
+{
+	if (!in || !lf || !ctable) return JP_ERR_ARG;
+	CtxGuard g; JP_TRY(acquire(-1, &g.c)); begin_call(*g.c);
+	return debug_lf(*g.c, in, nlen, lf, ctable);
+}
+int jp_bwt_debug_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
+{
+	if (!in || !sa || n < 0) return JP_ERR_ARG;
+	CtxGuard g; JP_TRY(acquire(-1, &g.c)); begin_call(*g.c);
+	return debug_suffix_array(*g.c, in, n, sa);
+}
+double jp_bwt_debug_gather_rate(uint64_t table_bytes, int32_t chains, int32_t steps, int dependent)
+{
+	CtxGuard g; int rc = acquire(-1, &g.c); if (rc != JP_OK) return rc; begin_call(*g.c);
+	return debug_gather_rate(*g.c, table_bytes, chains, steps, dependent);
+}
+
+}

@@ -1,0 +1,181 @@
+// radix_sort.cuh -- hand-written LSD radix sort of (64-bit key, 32-bit value) pairs for sm_100a.
+//
+// This is the "radix-bucketed" half of the forward transform: it orders suffixes by their packed
+// prefix keys and, in every doubling round, (group, rank-of-continuation) keys. 8-bit digits, stable.
+// One pass = per-tile digit histogram -> per-digit exclusive scan over tiles -> ranked scatter. The scatter
+// ranks keys inside a warp with match.any (no atomics, stable), re-orders the tile in shared memory so that
+// every digit's run leaves as coalesced stores, and adds the tile's global offsets.
+// No inter-block dependency (no look-back spin) -- a pass cannot hang.
+#pragma once
+#include "common.cuh"
+
+namespace jp {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS   = RS_THREADS / 32;
+constexpr int RS_ITEMS   = 16;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per block
+constexpr size_t RS_SMEM_SCATTER = (size_t)RS_TILE * (8 + 4);
+
+__device__ __forceinline__ u32 rs_digit(u64 k, int shift) { return (u32)(k >> shift) & 255u; }
+
+// tile_hist[tile][digit]
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ tile_hist)
+{
+	__shared__ u32 h[RS_WARPS][256];
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
+	__syncthreads();
+	const u32 base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+	u32* hw = h[w];
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = base + i * 32 + lane;
+		// keys of neighbouring suffixes often share a digit: aggregate inside the warp before the atomic
+		const u32 d = p < n ? rs_digit(keys[p], shift) : 256u;
+		const u32 peers = __match_any_sync(0xffffffffu, d);
+		if (d < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+	}
+	__syncthreads();
+	u32 s = 0;
+	#pragma unroll
+	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
+	tile_hist[(size_t)blockIdx.x * 256 + t] = s;
+}
+
+// block d: total of digit d over all tiles
+__global__ void __launch_bounds__(256) k_rs_totals(const u32* __restrict__ tile_hist, int tiles, u32* __restrict__ totals)
+{
+	__shared__ u32 ws[32];
+	const int d = blockIdx.x, t = threadIdx.x;
+	u32 s = 0;
+	for (int k = t; k < tiles; k += 256) s += tile_hist[(size_t)k * 256 + d];
+	u32 total;
+	block_incl_sum(s, ws, &total);
+	if (t == 0) totals[d] = total;
+}
+
+// block d: tile_hist[.][d] <- global offset of tile's first key with digit d
+__global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, int tiles, const u32* __restrict__ totals)
+{
+	__shared__ u32 ws[32];
+	const int d = blockIdx.x, t = threadIdx.x;
+	u32 total;
+	const u32 below = block_incl_sum(t < d ? totals[t] : 0u, ws, &total);
+	(void)below;
+	const u32 digit_base = total;                         // sum of totals[0..d)
+	const int per = (tiles + 255) / 256;
+	const int lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	u32 s = 0;
+	for (int k = lo; k < hi; k++) s += tile_hist[(size_t)k * 256 + d];
+	u32 tt;
+	const u32 inc = block_incl_sum(s, ws, &tt);
+	u32 run = digit_base + inc - s;
+	for (int k = lo; k < hi; k++) {
+		const size_t a = (size_t)k * 256 + d;
+		const u32 v = tile_hist[a];
+		tile_hist[a] = run;
+		run += v;
+	}
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin,
+                                                           u64* __restrict__ kout, u32* __restrict__ vout,
+                                                           const u32* __restrict__ tile_off, u32 n, int shift)
+{
+	extern __shared__ __align__(16) u8 rs_smem[];
+	u64* skey = reinterpret_cast<u64*>(rs_smem);
+	u32* sval = reinterpret_cast<u32*>(rs_smem + (size_t)RS_TILE * 8);
+	__shared__ u32 wcnt[RS_WARPS][256];
+	__shared__ u32 bin_start[256];
+	__shared__ u32 g_off[256];
+	__shared__ u32 ws[32];
+
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	const u32 lt = lanemask_lt();
+	const u32 tile_base = blockIdx.x * RS_TILE;
+	const u32 valid = min((u32)RS_TILE, n - tile_base);
+	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+
+	u64 key[RS_ITEMS];
+	u32 val[RS_ITEMS];
+	const u32 wbase = tile_base + w * (32 * RS_ITEMS);
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = wbase + i * 32 + lane;
+		const bool ok = p < n;
+		key[i] = ok ? kin[p] : ~0ull;     // padding sorts last inside the tile and is never written out
+		val[i] = ok ? vin[p] : 0u;
+	}
+	__syncthreads();
+
+	u32 rank[RS_ITEMS];
+	u32* mycnt = wcnt[w];
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 d = rs_digit(key[i], shift);
+		const u32 peers = __match_any_sync(0xffffffffu, d);
+		const u32 below = __popc(peers & lt);
+		u32 before = 0;
+		if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
+		before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+		rank[i] = before + below;
+		__syncwarp();
+	}
+	__syncthreads();
+
+	// digit t: exclusive scan over warps, then over digits
+	u32 run = 0;
+	#pragma unroll
+	for (int k = 0; k < RS_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+	u32 total;
+	const u32 inc = block_incl_sum(run, ws, &total);
+	bin_start[t] = inc - run;
+	g_off[t] = tile_off[(size_t)blockIdx.x * 256 + t] - (inc - run);
+	__syncthreads();
+
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 d = rs_digit(key[i], shift);
+		const u32 pos = bin_start[d] + mycnt[d] + rank[i];
+		skey[pos] = key[i];
+		sval[pos] = val[i];
+	}
+	__syncthreads();
+
+	for (u32 j = t; j < valid; j += RS_THREADS) {
+		const u64 k = skey[j];
+		const u32 dst = g_off[rs_digit(k, shift)] + j;
+		kout[dst] = k;
+		vout[dst] = sval[j];
+	}
+}
+
+struct RadixBuffers {
+	u64* k[2]; u32* v[2];
+	u32* tile_hist;   // ceil(n / RS_TILE) * 256
+	u32* totals;      // 256
+};
+
+inline size_t radix_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+
+// Sorts pairs in (k[cur], v[cur]) by key bits [bit_lo, bit_hi); returns the index (0/1) of the buffers
+// holding the result, or a negative error code. launches is incremented per kernel.
+inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit_hi, cudaStream_t s, int* launches)
+{
+	if (n == 0) return cur;
+	// function attributes are per device; setting one is a host-only call
+	if (cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
+	const int tiles = (int)radix_tiles(n);
+	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+		k_rs_hist<<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist);
+		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, b.totals);
+		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, b.totals);
+		k_rs_scatter<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, n, shift);
+		*launches += 4;
+		cur ^= 1;
+	}
+	return cur;
+}
+
+} // namespace jp
