@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the BWT stage of Jampack on B200: MB/s of inverse (headline) and forward BWT on 64 MiB blocks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): inverse BWT of one 64 MiB markov2(seed=1) block with all 120 stored
+indices; one block per GPU per step (weak scaling: blocks are independent, no collective on the data path).
+The forward transform of the same block (configs[2]/[3] shape) is reported in the "forward" object.
+
+  value     MB/s (1e6 bytes of block per second) with the block resident in HBM, CUDA events around K steps
+  e2e       the same through the host C-ABI (jp_bwt_inverse): pinned host block in, pinned host block out,
+            both copies inside the timed region
+  roofline  the inverse walk (the two LF-walk kernels + ranking) against the measured HBM copy bandwidth of
+            MEASURED_PEAKS.json, at SURVEY.md 8d's 64 B of random sectors per byte; `rand_peak` is the random
+            32 B-sector gather rate measured live by the library's own micro-benchmark
+  cpu_baseline  the unmodified reference (oracle/_ref) on this box's host cores, block-parallel like
+            Jampack::Compress/Decompress (jampack.cpp:215-219, :313-317): one block per core
+
+--impl reference times only the reference CPU implementation (rank 0; other ranks exit).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MiB = 1 << 20
+TRAILER = 480
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--block-mib", type=int, default=64)
+    ap.add_argument("--kind", default="markov2")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-forward", action="store_true")
+    return ap.parse_args()
+
+
+# ---- clocks -------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(key):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)).get(key)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+# ---- the reference on the host cores (cpu_baseline leg and --impl reference) ---------------------------------
+def cpu_reference(direction, block, fwd_out, cores, steps=1, warmup=0, budget_s=300.0):
+    """Block-parallel shape: `cores` independent copies of the block, one reference call per core.
+    Returns dict(value MB/s, ms_per_step, steps, kind, cores, sample)."""
+    import oracle                                    # checker / baseline only -- never on the product path
+    ref = oracle.ref()
+    kind = "reference" if ref is not None else "port"
+    n = block.size
+    P = cores
+    outs = [np.empty(n + TRAILER, dtype=np.uint8) for _ in range(P)]
+    src = block if direction == "forward" else fwd_out
+    pp = (C.c_void_p * P)(*[src.ctypes.data] * P)
+    po = (C.c_void_p * P)(*[o.ctypes.data for o in outs])
+    lens = (C.c_int32 * P)(*[src.size] * P)
+
+    def one_step():
+        if ref is not None:
+            if direction == "forward":
+                return ref.ref_bwt_forward_batch(pp, lens, po, P, P)
+            return ref.ref_bwt_inverse_batch(pp, lens, po, P, P, 1)
+        t0 = time.perf_counter()                     # the C restatement, serial per block, thread per block
+        th = [threading.Thread(target=(oracle.forward if direction == "forward" else oracle.inverse), args=(src, "port"))
+              for _ in range(P)]
+        [t.start() for t in th]; [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    times = []
+    t_first = one_step() if warmup > 0 else None
+    if t_first is not None and (warmup + steps) * t_first > budget_s:
+        warmup, steps = 1, max(1, int(budget_s / t_first) - 1)
+    for _ in range(max(warmup - 1, 0)):
+        one_step()
+    for _ in range(steps):
+        times.append(one_step())
+    want = block if direction == "inverse" else fwd_out
+    ok = all((o[: want.size] == want).all() for o in outs[:2])
+    sec = sum(times) / len(times)
+    return {"value": round(P * n / sec / 1e6, 2), "unit": "MB/s", "cores": P, "kind": kind, "ms_per_step": round(sec * 1e3, 1),
+            "steps": len(times), "output_matches": bool(ok),
+            "sample": f"{P} x {n >> 20} MiB {direction} blocks, one per core (block-parallel, jampack.cpp:215-219), {len(times)} batch(es)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    import oracle
+    import synth
+    n = args.block_mib * MiB
+    T = synth.gen(args.kind, n, args.seed)
+    fwd = oracle.forward(T, "ref" if oracle.ref() is not None else "port")
+    cores = os.cpu_count() or 1
+    inv = cpu_reference("inverse", T, fwd, cores, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "inv BWT MB/s", "value": inv["value"], "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": inv["steps"], "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": inv["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, n), "cpu_baseline": {k: inv[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": inv["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cores": cores}
+    if not args.no_forward:
+        f = cpu_reference("forward", T, fwd, cores, steps=1, warmup=0)
+        line["forward"] = {"value": f["value"], "unit": "MB/s", "ms_per_step": f["ms_per_step"],
+                           "cpu_baseline": {k: f[k] for k in ("value", "unit", "cores", "kind", "sample")}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n):
+    return {"workload": f"inverse BWT of one {args.block_mib} MiB {args.kind}(seed={args.seed}) block per GPU per step, "
+                        "all 120 stored primary indices (BASELINE.json configs[1])",
+            "block_bytes": n, "units": 120,
+            "l2": "per-step working set 6N = %d MB exceeds the 126 MB L2; no explicit flush" % (6 * n // 10**6)}
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    import jampack_b200 as jp
+    import synth
+    from jampack_b200 import build, shard
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this stage has no CPU path"}))
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+    jp.set_devices([local])
+
+    n = args.block_mib * MiB
+    nlen = n - n % 120
+    T = synth.gen(args.kind, n, args.seed)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # -- inputs resident in HBM
+    d_T = torch.from_numpy(T).to(dev)
+    d_B = torch.zeros(n + TRAILER, dtype=torch.uint8, device=dev)
+    d_back = torch.zeros(n, dtype=torch.uint8, device=dev)
+    jp.forward_device(d_T, d_B)
+    B = d_B.cpu().numpy()
+    parity = {"round_trip": None, "forward_matches_golden": None}
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+        for c in gold.get("big", []):
+            if (c["kind"], c["len"], c["seed"]) == (args.kind, n, args.seed):
+                parity["forward_matches_golden"] = ("%016x" % synth.fnv(B)) == c["fnv_all"]
+    except Exception:  # noqa: BLE001
+        pass
+
+    def timed_device(fn, stat_keys):
+        for _ in range(W):
+            fn()
+        acc = {k: 0.0 for k in stat_keys}
+        launches = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+            st = jp.last_stats()
+            launches += st.kernel_launches
+            for k in stat_keys:
+                acc[k] += st.ms_phase[k]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return ms, acc, launches, jp.last_stats().asdict()
+
+    def timed_host(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return ms
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    # -- inverse: device-resident, then end to end through the host C-ABI with pinned blocks
+    inv_ms, inv_acc, inv_launches, inv_stats = timed_device(lambda: jp.inverse_device(d_B, d_back), [0, 1, 2, 3, 4])
+    parity["round_trip"] = bool(torch.equal(d_back, d_T))
+    h_in, h_out = jp.PinnedBlock(n + TRAILER), jp.PinnedBlock(n + TRAILER)
+    h_in.array[:] = B
+    inv_e2e_ms = timed_host(lambda: jp.inverse(h_in.array, out=h_out.array))
+    parity["round_trip"] = parity["round_trip"] and bool((h_out.array[:n] == T).all())
+
+    fwd = None
+    if not args.no_forward:
+        fwd_ms, fwd_acc, fwd_launches, fwd_stats = timed_device(lambda: jp.forward_device(d_T, d_B), [0, 1, 2, 3, 4])
+        h_in.array[:n] = T
+        fwd_e2e_ms = timed_host(lambda: jp.forward(h_in.array[:n], out=h_out.array))
+        parity["forward_host_equals_device"] = bool((h_out.array[: n + TRAILER] == B).all())
+        fwd = (fwd_ms, fwd_acc, fwd_launches, fwd_stats, fwd_e2e_ms)
+
+    clk = clocks.stop() if rank == 0 else None
+
+    inv_ms_max, total_bytes = shard.reduce_step_stats(inv_ms, n * K, dev)
+    inv_e2e_max, _ = shard.reduce_step_stats(inv_e2e_ms, n * K, dev)
+    if fwd:
+        fwd_ms_max, _ = shard.reduce_step_stats(fwd[0], n * K, dev)
+        fwd_e2e_max, _ = shard.reduce_step_stats(fwd[4], n * K, dev)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        rand_rate = jp.debug_gather_rate(1 << 30, 148 * 2048, 256, True)          # sectors/s, 1 GiB table
+        walk_ms = (inv_acc[2] + inv_acc[3] + inv_acc[4]) / K                        # both walk kernels + ranking
+        algo_bytes = 64.0 * nlen                                                    # 2 random sectors / byte
+        achieved = algo_bytes / (walk_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_inv_walk_len + k_inv_rank + k_inv_walk_emit", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch_pair": algo_bytes, "ms_per_step": round(walk_ms, 4),
+                "traffic": ncu_traffic("inverse_walk"),
+                "rand_peak": round(rand_rate * 32 / 1e9, 1), "rand_unit": "GB/s of 32 B sectors (live micro-benchmark, 1 GiB table)",
+                "frac_of_rand": round(achieved / (rand_rate * 32 / 1e9), 4),
+                "phases_ms": {k: round(v / K, 4) for k, v in zip(("hist_ctable", "lf_build", "walk_len", "rank", "walk_emit"), inv_acc.values())}}
+        line = {"metric": "inv BWT MB/s", "value": round(total_bytes / (inv_ms_max * 1e-3) / 1e6, 1), "unit": "MB/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(inv_ms_max / K, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, n),
+                "e2e": {"value": round(total_bytes / (inv_e2e_max * 1e-3) / 1e6, 1), "unit": "MB/s", "ms_per_step": round(inv_e2e_max / K, 4),
+                        "h2d_bytes_per_step": n + TRAILER, "d2h_bytes_per_step": n, "host_memory": "pinned"},
+                "gpu_launches": inv_launches, "clocks": clk, "roofline": roof, "parity": parity,
+                "inverse_stats": {k: inv_stats[k] for k in ("subchains", "subchain_spacing", "device_bytes", "kernel_launches")},
+                "host_cores": os.cpu_count()}
+        if fwd:
+            st = fwd[3]
+            sum_a = sum(st["active_fraction"])
+            a_fwd = nlen * (38 + 24) + 80.0 * nlen * sum_a                          # SURVEY.md 8d counted model
+            r_fwd = nlen * 32 + 64.0 * nlen * sum_a
+            f_ms = fwd_ms_max / K
+            line["forward"] = {"value": round(total_bytes / (fwd_ms_max * 1e-3) / 1e6, 1), "unit": "MB/s", "ms_per_step": round(f_ms, 4),
+                               "e2e": {"value": round(total_bytes / (fwd_e2e_max * 1e-3) / 1e6, 1), "unit": "MB/s",
+                                       "h2d_bytes_per_step": n, "d2h_bytes_per_step": n + TRAILER, "host_memory": "pinned"},
+                               "gpu_launches": fwd[2], "rounds": st["rounds"], "active_fraction": st["active_fraction"],
+                               "symbol_bits": st["symbol_bits"], "initial_depth": st["initial_depth"], "device_bytes": st["device_bytes"],
+                               "roofline": {"bound": "hbm", "achieved": round(a_fwd / (f_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                                            "frac": round(a_fwd / (f_ms * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": a_fwd,
+                                            "random_bytes": r_fwd, "traffic": ncu_traffic("forward")},
+                               "phases_ms": {k: round(v / K, 4) for k, v in zip(("keys", "initial_sort", "initial_ranks", "rounds", "emit"), fwd[1].values())}}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cb = cpu_reference("inverse", T, B, cores)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "output_matches")}
+            if fwd:
+                cf = cpu_reference("forward", T, B, cores)
+                line["forward"]["cpu_baseline"] = {k: cf[k] for k in ("value", "unit", "cores", "kind", "sample", "output_matches")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

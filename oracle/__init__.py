@@ -55,16 +55,6 @@ def port():
         L.jpo_suffix_array_export.restype = C.c_int
         L.jpo_check_suffix_array.argtypes = [_u8p, _i32p, C.c_int32]
         L.jpo_check_suffix_array.restype = C.c_int
-        for name in ("uniform", "markov2", "repetitive"):
-            f = getattr(L, "jpo_gen_" + name)
-            f.argtypes = [_u8p, C.c_int64, C.c_uint64]
-            f.restype = None
-        for name in ("alla", "kat_quadratic", "kat_extremes"):
-            f = getattr(L, "jpo_gen_" + name)
-            f.argtypes = [_u8p, C.c_int64]
-            f.restype = None
-        L.jpo_fnv1a64.argtypes = [_u8p, C.c_int64]
-        L.jpo_fnv1a64.restype = C.c_uint64
         _port = L
     return _port
 
@@ -90,23 +80,15 @@ def ref():
     return _ref
 
 
-# ---- generators ----------------------------------------------------------
+# ---- generators live in synth/ (shared with bench.py); re-exported for the tests ------------------------
 def gen(kind, n, seed=0):
-    """kind in uniform|markov2|repetitive|alla|kat_quadratic|kat_extremes -> np.uint8[n]"""
-    T = np.empty(int(n), dtype=np.uint8)
-    if n == 0:
-        return T
-    L = port()
-    if kind in ("uniform", "markov2", "repetitive"):
-        getattr(L, "jpo_gen_" + kind)(_ptr(T), int(n), int(seed))
-    else:
-        getattr(L, "jpo_gen_" + kind)(_ptr(T), int(n))
-    return T
+    import synth
+    return synth.gen(kind, n, seed)
 
 
 def fnv(a):
-    a = np.ascontiguousarray(a, dtype=np.uint8)
-    return int(port().jpo_fnv1a64(_ptr(a), a.size))
+    import synth
+    return synth.fnv(a)
 
 
 # ---- stage calls; `impl` is "port" or "ref" -------------------------------------------------------

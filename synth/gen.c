@@ -1,6 +1,6 @@
-/* TEST INFRASTRUCTURE ONLY -- synthetic block generators and the FNV-1a hash used to pin
- * known-answer values. Definitions follow SURVEY.md Appendix B exactly (the reference ships
- * no data of its own). Nothing here is on the product path. */
+/* Synthetic block generators (BASELINE.json configs) and the FNV-1a hash used to pin known-answer
+ * values. Definitions follow SURVEY.md Appendix B exactly (the reference ships no data of its own).
+ * Input generation only: neither the product path nor the oracle's algorithm lives here. */
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
@@ -14,14 +14,14 @@ static inline uint64_t sm64_next(uint64_t* x)
 	return z ^ (z >> 31);
 }
 
-void jpo_gen_uniform(uint8_t* T, int64_t n, uint64_t seed)
+void jps_gen_uniform(uint8_t* T, int64_t n, uint64_t seed)
 {
 	uint64_t x = seed;
 	for (int64_t i = 0; i < n; i++) T[i] = (uint8_t)(sm64_next(&x) >> 56);
 }
 
 /* order-2 Markov text over a 64-symbol printable alphabet, geometric choice among 8 successors */
-void jpo_gen_markov2(uint8_t* T, int64_t n, uint64_t seed)
+void jps_gen_markov2(uint8_t* T, int64_t n, uint64_t seed)
 {
 	uint64_t x = seed;
 	uint8_t* nxt = (uint8_t*)malloc(64 * 64 * 8);
@@ -38,7 +38,7 @@ void jpo_gen_markov2(uint8_t* T, int64_t n, uint64_t seed)
 }
 
 /* period-1021 motif over {a,b,c,d}, one flipped bit every 64 KiB */
-void jpo_gen_repetitive(uint8_t* T, int64_t n, uint64_t seed)
+void jps_gen_repetitive(uint8_t* T, int64_t n, uint64_t seed)
 {
 	uint64_t x = seed;
 	uint8_t m[1021];
@@ -47,22 +47,22 @@ void jpo_gen_repetitive(uint8_t* T, int64_t n, uint64_t seed)
 	for (int64_t i = 65536; i < n; i += 65536) T[i] ^= 1;
 }
 
-void jpo_gen_alla(uint8_t* T, int64_t n)
+void jps_gen_alla(uint8_t* T, int64_t n)
 {
 	for (int64_t i = 0; i < n; i++) T[i] = 'a';
 }
 
 /* KAT-A/B/C: T[i] = (i*i + 3i) & 255 ; KAT-E: i%3==0 ? 0 : i%5==0 ? 255 : i&1 */
-void jpo_gen_kat_quadratic(uint8_t* T, int64_t n)
+void jps_gen_kat_quadratic(uint8_t* T, int64_t n)
 {
 	for (int64_t i = 0; i < n; i++) T[i] = (uint8_t)((i * i + 3 * i) & 255);
 }
-void jpo_gen_kat_extremes(uint8_t* T, int64_t n)
+void jps_gen_kat_extremes(uint8_t* T, int64_t n)
 {
 	for (int64_t i = 0; i < n; i++) T[i] = (i % 3 == 0) ? 0 : (i % 5 == 0) ? 255 : (uint8_t)(i & 1);
 }
 
-uint64_t jpo_fnv1a64(const uint8_t* p, int64_t n)
+uint64_t jps_fnv1a64(const uint8_t* p, int64_t n)
 {
 	uint64_t h = 0xcbf29ce484222325ull;
 	for (int64_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x100000001b3ull; }

@@ -1,0 +1,273 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C-ABI of include/jp_bwt.h
+(ctypes, jampack_b200/__init__.py) and is compared bit-for-bit with the oracle: the compiled reference
+(oracle/_ref) when it travelled with the repo, else the C restatement; plus the committed golden vectors."""
+import hashlib
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MiB = 1 << 20
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def jp():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import jampack_b200
+    from jampack_b200 import build
+    build.build()
+    assert jampack_b200.device_count() >= 1
+    return jampack_b200
+
+
+def _impl(orc):
+    return "ref" if orc.ref() is not None else "port"
+
+
+SMALL = [("kat_quadratic", 240, 0), ("kat_quadratic", 250, 0), ("alla", 360, 0), ("kat_extremes", 240, 0),
+         ("kat_quadratic", 120, 0), ("uniform", 121, 7), ("markov2", 4093, 9), ("repetitive", 70000, 3),
+         ("uniform", 5000, 4), ("markov2", 65536 + 120, 3), ("uniform", 4096 * 3 + 1, 5)]
+MEDIUM = [("markov2", MiB, 1), ("uniform", MiB, 2), ("repetitive", MiB, 3), ("alla", MiB, 0), ("markov2", 3 * MiB + 77, 4)]
+
+
+@pytest.mark.parametrize("kind,n,seed", SMALL + MEDIUM)
+def test_forward_bit_exact(jp, orc, kind, n, seed):
+    T = orc.gen(kind, n, seed)
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    got = jp.forward(T, prefill=0x5C)
+    assert got.size == n + 480
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("kind,n,seed", SMALL + MEDIUM)
+def test_inverse_bit_exact_and_cross(jp, orc, kind, n, seed):
+    T = orc.gen(kind, n, seed)
+    B = orc.forward(T, _impl(orc))
+    assert (jp.inverse(B) == T).all()                       # reference forward -> our inverse
+    ours = jp.forward(T)
+    assert (orc.inverse(ours, _impl(orc), threads=4) == T).all()   # our forward -> reference inverse
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 119])
+def test_short_blocks_copy_and_leave_trailer(jp, orc, n):
+    """len < 120: nothing is transformed and the 480 trailer bytes are NOT written (bwt.cpp:35, SURVEY finding 7)."""
+    T = orc.gen("uniform", n, 3)
+    out = jp.forward(T, prefill=0xAB)
+    assert (out[:n] == T).all() and (out[n:] == 0xAB).all()
+    assert (out == orc.forward(T, _impl(orc), prefill=0xAB)).all()
+    back = jp.inverse(out)
+    assert back.size == n and (back == T).all()
+
+
+def test_zero_runs_and_extreme_bytes(jp, orc):
+    """0x00 runs at the end are where zero-padded prefix keys would tie with the end of string."""
+    T = orc.gen("markov2", 120 * 300, 8)
+    T[-500:] = 0
+    T[1000:1400] = 0
+    T[2000:2100] = 255
+    want = orc.forward(T, _impl(orc))
+    assert (jp.forward(T) == want).all()
+    assert (jp.inverse(want) == T).all()
+    Z = np.zeros(120 * 50, dtype=np.uint8)
+    assert (jp.forward(Z) == orc.forward(Z, _impl(orc))).all()
+    F = np.full(120 * 50 + 3, 255, dtype=np.uint8)
+    assert (jp.forward(F) == orc.forward(F, _impl(orc))).all()
+
+
+def test_golden_vectors(jp, orc, golden):
+    """tests/golden/kat.json: outputs of the unmodified reference (incl. SURVEY.md Appendix B indices)."""
+    for c in golden["cases"]:
+        T = orc.gen(c["kind"], c["len"], c["seed"])
+        got = jp.forward(T)
+        if "out_hex" in c:
+            want = np.frombuffer(bytes.fromhex(c["out_hex"]), dtype=np.uint8)
+            assert (got[: want.size] == want).all(), c["name"]
+        assert "%016x" % orc.fnv(got[: c["len"]]) == c["fnv_bwt"], c["name"]
+        if c["nlen"]:
+            assert "%016x" % orc.fnv(got) == c["fnv_all"], c["name"]
+            assert [int(x) for x in orc.indices(got)] == c["indices"], c["name"]
+            assert (jp.inverse(got) == T).all(), c["name"]
+
+
+def test_golden_full_size_blocks(jp, orc, golden):
+    """BASELINE.json configs 2, 3 and 5 at full size (64 MiB x4, 256 MiB): forward hash + all 120 indices
+    against the reference's, and the round trip."""
+    assert len(golden.get("big", [])) == 5
+    for c in golden["big"]:
+        T = orc.gen(c["kind"], c["len"], c["seed"])
+        assert "%016x" % orc.fnv(T) == c["fnv_in"]
+        got = jp.forward(T)
+        st = jp.last_stats()
+        assert "%016x" % orc.fnv(got[: c["len"]]) == c["fnv_bwt"], c["name"]
+        assert "%016x" % orc.fnv(got) == c["fnv_all"], c["name"]
+        assert [int(x) for x in orc.indices(got)] == c["indices"], c["name"]
+        back = jp.inverse(got)
+        si = jp.last_stats()
+        assert (back == T).all(), c["name"]
+        # inverse stays within 6N + o(N): in (N+480) + out (N) are the caller's, the workspace is lf (4N) + side tables
+        assert si.device_bytes <= 4 * c["nlen"] + c["nlen"] // 4 + (1 << 20), (c["name"], si.device_bytes)
+        assert st.rounds <= 40
+
+
+def test_lf_table_is_inverse_of_reference_map(jp, orc):
+    """Rows a7/a8 of SURVEY.md 8a: C table == bwt.cpp:141-169, LF == inverse permutation of Map (bwt.cpp:171-174)."""
+    for kind, n, seed in [("markov2", 120 * 1000, 1), ("uniform", 65536 * 2 + 120 * 5, 2), ("alla", 12000, 0)]:
+        T = orc.gen(kind, n, seed)
+        B = orc.forward(T, _impl(orc))
+        nlen = n - n % 120
+        idx = int(orc.indices(B)[0])
+        Map, Ct = orc.build_map(B[:nlen], nlen, idx)
+        lf, ct = jp.debug_lf(B[:nlen])
+        assert (ct == Ct).all()
+        i = np.arange(nlen)
+        assert (Map[lf - 1] == i + (i >= idx)).all()
+
+
+def test_suffix_array_contract(jp, orc):
+    """Row a2: the suffix array itself (divsufsort contract), checked by brute force on a small block."""
+    rng = np.random.default_rng(5)
+    T = rng.integers(0, 3, 3000).astype(np.uint8)
+    T[1500:] = T[:1500]
+    sa = jp.debug_suffix_array(T)
+    b = T.tobytes()
+    assert sa.tolist() == sorted(range(T.size), key=lambda i: b[i:])
+    T2 = orc.gen("markov2", 200000, 12)
+    assert (jp.debug_suffix_array(T2) == orc.suffix_array(T2)).all()
+
+
+def test_stage_interface_mirror(jp, orc):
+    """BlockSort::Bwt through Buffer/Options, incl. the size side effects (bwt.cpp:27, :77-78)."""
+    n = 120 * 777 + 13
+    T = orc.gen("markov2", n, 21)
+    cap = int(n * 1.05) + 480
+    Input = jp.Buffer(np.zeros(cap, dtype=np.uint8), n)
+    Input.block[:n] = T
+    Output = jp.Buffer(np.zeros(cap, dtype=np.uint8), 0)
+    bwt = jp.Bwt()
+    bwt.ForwardBwt(Input, Output)
+    assert Output.size[0] == n + 480 and Input.size[0] == n
+    assert (Output.block[: n + 480] == orc.forward(T, _impl(orc))).all()
+    Back = jp.Buffer(np.zeros(cap, dtype=np.uint8), 0)
+    bwt.InverseBwt(Output, Back, jp.Options(Threads=8))
+    assert Output.size[0] == n and Back.size[0] == n           # InverseBwt shrinks *Input.size in place
+    assert (Back.block[:n] == T).all()
+
+
+def test_inverse_rejects_corrupt_input(jp, orc):
+    T = orc.gen("markov2", 120 * 2000, 5)
+    n = T.size
+    B = orc.forward(T, _impl(orc)).copy()
+    bad = B.copy()
+    bad[n + 4 * 7: n + 4 * 7 + 4] = np.frombuffer(np.int32(n + 1).tobytes(), dtype=np.uint8)   # out of range
+    with pytest.raises(jp.BwtError) as e:
+        jp.inverse(bad)
+    assert e.value.rc == -5
+    bad = B.copy()
+    bad[n + 4 * 9: n + 4 * 9 + 4] = bad[n + 4 * 8: n + 4 * 8 + 4]                                # duplicated index
+    with pytest.raises(jp.BwtError):
+        jp.inverse(bad)
+    bad = B.copy()
+    bad[n + 4 * 50: n + 4 * 50 + 4] = np.frombuffer(np.int32(12345).tobytes(), dtype=np.uint8)   # wrong but in range
+    with pytest.raises(jp.BwtError) as e:
+        jp.inverse(bad)
+    assert e.value.rc == -6
+    assert (jp.inverse(B) == T).all()                           # the context is still healthy afterwards
+
+
+def test_device_resident_entry_points(jp, orc):
+    import torch
+    T = orc.gen("markov2", 4 * MiB + 50, 31)
+    want = orc.forward(T, _impl(orc))
+    d_in = torch.from_numpy(T).cuda()
+    d_out = jp.forward_device(d_in)
+    st = jp.last_stats()
+    assert st.kernel_launches > 0 and st.ms_total > 0
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy() == want).all()
+    d_back = jp.inverse_device(d_out)
+    assert (d_back.cpu().numpy()[: T.size] == T).all()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        d_back2 = jp.inverse_device(d_out)
+    s.synchronize()
+    assert torch.equal(d_back, d_back2)
+
+
+def test_pinned_host_blocks(jp, orc):
+    n = 2 * MiB
+    T = orc.gen("uniform", n, 77)
+    src = jp.PinnedBlock(n + 480)
+    dst = jp.PinnedBlock(n + 480)
+    src.array[:n] = T
+    out = jp.forward(src.array[:n], out=dst.array)
+    assert (out == orc.forward(T, _impl(orc))).all()
+    src.free(); dst.free()
+
+
+def test_concurrent_calls_are_reentrant(jp, orc):
+    """The reference calls its stage from an OpenMP team, one block per thread (jampack.cpp:215-219)."""
+    blocks = [orc.gen("markov2", MiB + 120 * i, 40 + i) for i in range(8)]
+    wants = [orc.forward(b, _impl(orc)) for b in blocks]
+    outs = [None] * len(blocks)
+    errs = []
+
+    def work(i):
+        try:
+            f = jp.forward(blocks[i])
+            outs[i] = (f, jp.inverse(f))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(blocks))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i, b in enumerate(blocks):
+        assert (outs[i][0] == wants[i]).all() and (outs[i][1] == b).all()
+
+
+def test_linearity_free_properties_at_scale(jp, orc):
+    """Size-independent properties on a block nobody has a golden hash for: the BWT is a permutation of the
+    block's bytes, the indices are distinct rows in [1, nlen], and inverse(forward(x)) == x."""
+    n = 96 * MiB + 119
+    T = orc.gen("markov2", n, 4242)
+    out = jp.forward(T)
+    nlen = n - n % 120
+    assert (np.bincount(out[:nlen], minlength=256) == np.bincount(T[:nlen], minlength=256)).all()
+    assert (out[nlen:n] == T[nlen:]).all()
+    I = orc.indices(out)
+    assert I.min() >= 1 and I.max() <= nlen and np.unique(I).size == 120
+    assert (jp.inverse(out) == T).all()
+
+
+def test_reference_pipeline_with_shim_is_byte_identical(jp, orc, golden, tmp_path):
+    """BASELINE.json configs[0]: the reference CLI with our stage linked in place of bwt.cpp must emit the same
+    .jam bytes as the unmodified reference (sha256 pinned in tests/golden/kat.json), and each must decode the other's."""
+    shim = os.path.join(ROOT, "oracle", "_ref", "Jampack_shim")
+    ref = os.path.join(ROOT, "oracle", "_ref", "Jampack_ref")
+    if not (os.path.isfile(shim) and os.path.isfile(ref)):
+        pytest.skip("oracle/_ref binaries did not travel (built only where /root/reference exists)")
+    T = orc.gen("markov2", 8 * MiB, 1)
+    src = tmp_path / "in.bin"
+    T.tofile(src)
+    assert hashlib.sha256(T.tobytes()).hexdigest() == golden["config1"]["input_sha256"]
+    jam_s, jam_r = tmp_path / "shim.jam", tmp_path / "ref.jam"
+    subprocess.run([shim, "c", str(src), str(jam_s), "-t4"], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    sha = hashlib.sha256(jam_s.read_bytes()).hexdigest()
+    assert jam_s.stat().st_size == golden["config1"]["jam_bytes"]
+    assert sha == golden["config1"]["jam_sha256"]
+    subprocess.run([ref, "c", str(src), str(jam_r), "-t4"], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    assert jam_r.read_bytes() == jam_s.read_bytes()
+    back_s, back_r = tmp_path / "back_s.bin", tmp_path / "back_r.bin"
+    subprocess.run([shim, "d", str(jam_r), str(back_s), "-t4"], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    subprocess.run([ref, "d", str(jam_s), str(back_r), "-t4"], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    assert back_s.read_bytes() == T.tobytes() and back_r.read_bytes() == T.tobytes()
+    # single-block decode mode (-T, jampack.cpp:249-282) goes through the same stage from the main thread
+    back_t = tmp_path / "back_t.bin"
+    subprocess.run([shim, "d", str(jam_s), str(back_t), "-T"], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    assert back_t.read_bytes() == T.tobytes()
