@@ -92,6 +92,13 @@ static int create_ctx(int device, Ctx** out)
 	std::unique_ptr<Ctx> c(new Ctx());
 	c->device = device;
 	JP_CUDA(cudaSetDevice(device));
+	{
+		// The LF walk and the rank gathers use 4 bytes of every sector they touch: ask L2 to fetch single 32 B
+		// sectors on a miss instead of promoting to 64/128 B (ncu: 3.3 DRAM sectors per gather with the default).
+		size_t gran = 32;
+		if (const char* e = getenv("JP_BWT_L2_FETCH")) { long v = atol(e); if (v == 32 || v == 64 || v == 128) gran = (size_t)v; }
+		if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();   // a hint; never fatal
+	}
 	JP_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	JP_CUDA(cudaMallocHost(&c->h_small, 64 * sizeof(int)));
 	for (auto& e : c->ev) JP_CUDA(cudaEventCreate(&e));
