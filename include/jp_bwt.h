@@ -70,6 +70,11 @@ int jp_bwt_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, in
  * neighbour stage would call. */
 int jp_bwt_forward_device(const uint8_t* d_in, int32_t len, uint8_t* d_out, int device, void* stream);
 int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream);
+/* Same, but d_in is CONSUMED: once the LF table is built the input block is dead (the reference's caller swaps
+ * streams and overwrites it, jampack.cpp:50-51), so its bytes hold the sub-chain records and the whole call stays
+ * within in + out + 4N table = 6N of device memory (+ N/64 of histograms). The host entry point always works
+ * this way on its own device copy. */
+int jp_bwt_inverse_device_consume(uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream);
 
 /* ---- device selection (block sharding) ---------------------------------------------
  * Default: every visible device, or the list in the environment variable JP_BWT_DEVICES ("0,1,2").

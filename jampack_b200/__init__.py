@@ -60,6 +60,7 @@ def lib():
         L.jp_bwt_inverse.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, _i32p]
         L.jp_bwt_forward_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p]
         L.jp_bwt_inverse_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p]
+        L.jp_bwt_inverse_device_consume.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p]
         L.jp_bwt_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
         L.jp_bwt_device_count.argtypes = []
         L.jp_bwt_host_alloc.argtypes = [C.c_uint64]
@@ -79,7 +80,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device",
+EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device", "jp_bwt_inverse_device_consume",
            "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free",
            "jp_bwt_last_stats", "jp_bwt_strerror", "jp_bwt_last_error_detail", "jp_bwt_version",
            "jp_bwt_debug_lf", "jp_bwt_debug_suffix_array", "jp_bwt_debug_gather_rate"]
@@ -174,14 +175,15 @@ def forward_device(d_in, d_out=None):
     return d_out
 
 
-def inverse_device(d_in, d_out=None):
+def inverse_device(d_in, d_out=None, consume=False):
+    """consume=True lets the stage overwrite d_in with scratch data (stays within 6N of device memory)."""
     import torch
     assert d_in.is_cuda and d_in.dtype == torch.uint8 and d_in.is_contiguous()
     n = d_in.numel()
     if d_out is None:
         d_out = torch.zeros(max(n - TRAILER, 1), dtype=torch.uint8, device=d_in.device)
-    _check(lib().jp_bwt_inverse_device(d_in.data_ptr(), n, d_out.data_ptr(), d_in.device.index or 0, _stream_of(d_in)),
-           "jp_bwt_inverse_device")
+    fn = lib().jp_bwt_inverse_device_consume if consume else lib().jp_bwt_inverse_device
+    _check(fn(d_in.data_ptr(), n, d_out.data_ptr(), d_in.device.index or 0, _stream_of(d_in)), "jp_bwt_inverse_device")
     return d_out
 
 

@@ -103,18 +103,25 @@ constexpr int GS_SUB     = 16;
 constexpr int GS_TILE    = GS_THREADS * GS_SUB;
 struct GAgg { i32 mh; u32 ns; u32 ng; u32 pad; };
 
+// Group boundaries come either from the sorted keys (a key change) or, after the shared-memory segmented sort,
+// from the one-byte head flags it wrote.
 struct GFlags { bool head, nhead; };
-__device__ __forceinline__ GFlags group_flags(const u64* __restrict__ K, u32 j, u32 A)
+__device__ __forceinline__ GFlags group_flags(const u64* __restrict__ K, const u8* __restrict__ F, u32 j, u32 A)
 {
-	const u64 kj = K[j];
 	GFlags f;
-	f.head = (j == 0) || (K[j - 1] != kj);
-	f.nhead = (j + 1 == A) || (K[j + 1] != kj);
+	if (F) {
+		f.head = F[j] != 0;
+		f.nhead = (j + 1 == A) || (F[j + 1] != 0);
+	} else {
+		const u64 kj = K[j];
+		f.head = (j == 0) || (K[j - 1] != kj);
+		f.nhead = (j + 1 == A) || (K[j + 1] != kj);
+	}
 	return f;
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict__ K, const u32* __restrict__ P, u32 A,
-                                                           GAgg* __restrict__ agg)
+__global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict__ K, const u8* __restrict__ F,
+                                                           const u32* __restrict__ P, u32 A, GAgg* __restrict__ agg)
 {
 	__shared__ i32 smh[8];
 	__shared__ u32 sns[8], sng[8];
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict
 	for (int s = 0; s < GS_SUB; s++) {
 		const u32 j = base + s * GS_THREADS + t;
 		if (j < A) {
-			const GFlags f = group_flags(K, j, A);
+			const GFlags f = group_flags(K, F, j, A);
 			if (f.head) mh = max(mh, (i32)(P ? P[j] : j));
 			ns += !(f.head && f.nhead);
 			ng += (f.head && !f.nhead);
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg,
 	if (t == 1023) { out[0] = pns + ins; out[1] = png + ing; }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict__ K, const u32* __restrict__ V,
+__global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict__ K, const u8* __restrict__ F, const u32* __restrict__ V,
                                                           const u32* __restrict__ P, u32 A, const GAgg* __restrict__ agg,
                                                           int rank_bits, u32* __restrict__ ISA, u32* __restrict__ SA,
                                                           u64* __restrict__ Kn, u32* __restrict__ Vn, u32* __restrict__ Pn)
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict_
 		bool head = false, surv = false, shead = false;
 		u32 v = 0, p = 0;
 		if (j < A) {
-			const GFlags f = group_flags(K, j, A);
+			const GFlags f = group_flags(K, F, j, A);
 			head = f.head; surv = !(f.head && f.nhead); shead = f.head && !f.nhead;
 			v = V[j]; p = P ? P[j] : j;
 		}
@@ -221,7 +228,139 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict_
 	}
 }
 
-// ---- 5. doubling: fetch the rank of the continuation ---------------------------------------------------
+// ---- 5a. doubling round, small groups: gather + segmented sort in shared memory -------------------------
+// Groups are contiguous in the active set, so refining them is a SEGMENTED sort. Block c owns the groups whose
+// head lies in its window of SG_WIN slots; they end within two windows unless the last one is "large". The block
+// gathers key2 = ISA[s + h] for its (<= 4096) elements, sorts (local group id, key2) with an LSD radix sort that
+// never leaves shared memory (warp match.any ranking, same scheme as k_rs_scatter), writes the suffix ids back in
+// place and one head flag per element. One global read and one global write of 4 bytes per active suffix
+// replace the 7 global radix passes over 12-byte pairs of the composite-key route.
+constexpr int SG_THREADS = 256;
+constexpr int SG_ITEMS   = 16;
+constexpr int SG_CAP     = SG_THREADS * SG_ITEMS;   // 4096 elements sorted per block
+constexpr int SG_WIN     = SG_CAP / 2;              // window of group heads per block
+constexpr size_t SG_SMEM = (size_t)SG_CAP * (8 + 4);
+
+__global__ void __launch_bounds__(SG_THREADS) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
+                                                         const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+                                                         u8* __restrict__ F, u32* __restrict__ has_large, int* __restrict__ err)
+{
+	extern __shared__ __align__(16) u8 sg_smem[];
+	u64* skey = reinterpret_cast<u64*>(sg_smem);
+	u32* sval = reinterpret_cast<u32*>(sg_smem + (size_t)SG_CAP * 8);
+	__shared__ u32 wcnt[SG_THREADS / 32][256];
+	__shared__ u32 bin_start[256];
+	__shared__ u32 ws[32];
+	__shared__ u32 s_first, s_lasthead, s_end;
+
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	const u32 lt = lanemask_lt();
+	const u32 w0 = blockIdx.x * SG_WIN;
+	const u32 L = min(w0 + (u32)SG_WIN, A);
+	if (t == 0) { s_first = 0xffffffffu; s_lasthead = 0; s_end = 0xffffffffu; }
+	__syncthreads();
+	#pragma unroll
+	for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
+		const u32 j = w0 + i * SG_THREADS + t;
+		if (j < L) {
+			const u64 g = K[j] >> rank_bits;
+			if (j == 0 || (K[j - 1] >> rank_bits) != g) { atomicMin(&s_first, j); atomicMax(&s_lasthead, j); }
+		}
+	}
+	__syncthreads();
+	const u32 start = s_first;
+	if (start == 0xffffffffu) return;                 // the window lies inside a group owned by an earlier block
+	u32 end;
+	if (L == A) end = A;
+	else {
+		const u64 gl = K[L - 1] >> rank_bits;
+		const u32 lim = min(w0 + 2u * SG_WIN, A);
+		#pragma unroll
+		for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
+			const u32 j = L + i * SG_THREADS + t;
+			if (j < lim && (K[j] >> rank_bits) != gl) atomicMin(&s_end, j);
+		}
+		__syncthreads();
+		end = s_end;
+		if (end == 0xffffffffu) {
+			if (lim == A) end = A;
+			else { end = s_lasthead; if (t == 0) *has_large = 1u; }   // last group spans > a window: not ours
+		}
+	}
+	if (end <= start) return;
+	const u32 len = end - start;                      // <= SG_CAP by construction
+	const u64 g0 = K[start] >> rank_bits;
+	const u32 gmax = (u32)((K[end - 1] >> rank_bits) - g0);
+	const int bits = rank_bits + bit_length((u64)gmax);
+
+	u64 key[SG_ITEMS];
+	u32 val[SG_ITEMS];
+	#pragma unroll
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = w * (32 * SG_ITEMS) + i * 32 + lane;
+		key[i] = ~0ull; val[i] = 0;
+		if (e < len) {
+			const u32 j = start + e;
+			const u32 v = V[j];
+			u32 p = v + h;
+			if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+			val[i] = v;
+			key[i] = (((K[j] >> rank_bits) - g0) << rank_bits) | (u64)__ldg(&ISA[p]);
+		}
+	}
+
+	for (int shift = 0; shift < bits; shift += 8) {
+		for (int i = t; i < (SG_THREADS / 32) * 256; i += SG_THREADS) (&wcnt[0][0])[i] = 0;
+		__syncthreads();
+		u32 rank[SG_ITEMS];
+		u32* mycnt = wcnt[w];
+		#pragma unroll
+		for (int i = 0; i < SG_ITEMS; i++) {
+			const u32 d = rs_digit(key[i], shift);
+			const u32 peers = __match_any_sync(0xffffffffu, d);
+			const u32 below = __popc(peers & lt);
+			u32 before = 0;
+			if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
+			before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+			rank[i] = before + below;
+			__syncwarp();
+		}
+		__syncthreads();
+		u32 run = 0;
+		#pragma unroll
+		for (int k = 0; k < SG_THREADS / 32; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+		u32 total;
+		const u32 inc = block_incl_sum(run, ws, &total);
+		bin_start[t] = inc - run;
+		__syncthreads();
+		#pragma unroll
+		for (int i = 0; i < SG_ITEMS; i++) {
+			const u32 d = rs_digit(key[i], shift);
+			const u32 pos = bin_start[d] + mycnt[d] + rank[i];
+			skey[pos] = key[i];
+			sval[pos] = val[i];
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int i = 0; i < SG_ITEMS; i++) {
+			const u32 e = w * (32 * SG_ITEMS) + i * 32 + lane;
+			key[i] = skey[e];
+			val[i] = sval[e];
+		}
+		__syncthreads();
+	}
+	// after the loop the registers hold the sorted sequence in slot order and skey still holds the same data
+	#pragma unroll
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = w * (32 * SG_ITEMS) + i * 32 + lane;
+		if (e < len) {
+			V[start + e] = val[i];
+			F[start + e] = (e == 0 || skey[e - 1] != key[i]) ? 1 : 0;
+		}
+	}
+}
+
+// ---- 5b. doubling, large groups: fetch the rank of the continuation (then global radix sort) ---------------------------------------------------
 __global__ void __launch_bounds__(256) k_fwd_gather(u64* __restrict__ K, const u32* __restrict__ V, u32 A,
                                                     const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err)
 {
@@ -274,6 +413,7 @@ struct FwdBuffers {
 	RadixBuffers rb;
 	u32* P[2];
 	u32* ISA; u32* SA;
+	u8* F;
 	GAgg* agg;
 	FwdMeta* meta;
 	u32* counters;
@@ -285,15 +425,16 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	const size_t N = (size_t)n;
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
 	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + Arena::align(N * 4) +
-	               Arena::align(rtiles * 256 * 4) + Arena::align(256 * 4) + Arena::align(gtiles * sizeof(GAgg)) +
-	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64);
+	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align(gtiles * sizeof(GAgg)) +
+	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16);
 	JP_TRY(arena_reserve(c, total));
 	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
 	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
 	b.P[0] = arena_take<u32>(c, N); b.P[1] = arena_take<u32>(c, N);
 	b.ISA = arena_take<u32>(c, N + 1); b.SA = arena_take<u32>(c, N);
-	b.rb.tile_hist = arena_take<u32>(c, rtiles * 256);
+	b.rb.tile_hist = arena_take<u32>(c, (rtiles + 4) * 256);
 	b.rb.totals = arena_take<u32>(c, 256);
+	b.F = arena_take<u8>(c, N + 16);
 	b.agg = arena_take<GAgg>(c, gtiles);
 	b.meta = arena_take<FwdMeta>(c, 1);
 	b.counters = arena_take<u32>(c, 16);
@@ -302,13 +443,14 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 }
 
 // One grouping step over the sorted pairs in rb.k/v[cur]; survivors land in rb.k/v[cur^1] and P[pc^1].
-static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos, u32 A, int rank_bits, cudaStream_t s)
+static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos, bool use_flags, u32 A, int rank_bits, cudaStream_t s)
 {
 	const int tiles = (int)((A + GS_TILE - 1) / GS_TILE);
 	const u32* P = identity_pos ? nullptr : b.P[pc];
-	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], P, A, b.agg); JP_LAUNCH(c);
+	const u8* F = use_flags ? b.F : nullptr;
+	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, P, A, b.agg); JP_LAUNCH(c);
 	k_grp_scan_tiles<<<1, 1024, 0, s>>>(b.agg, tiles, b.counters); JP_LAUNCH(c);
-	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, b.SA,
+	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, b.SA,
 	                                          b.rb.k[cur ^ 1], b.rb.v[cur ^ 1], b.P[pc ^ 1]); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 8, b.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -337,6 +479,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0]); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
+	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
+	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
 	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, bits * depth, s, &c.launches);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
@@ -344,7 +488,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 
 	const int rank_bits = bit_length((u64)n);
 	int pc = 0;
-	JP_TRY(group_step(c, b, cur, pc, true, (u32)n, rank_bits, s));
+	JP_TRY(group_step(c, b, cur, pc, true, false, (u32)n, rank_bits, s));
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	int act = cur ^ 1; pc ^= 1;
 	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
@@ -356,11 +500,29 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
 		st->active_fraction[rounds] = (float)((double)A / (double)n);
 		sectors += 2ull * A;
-		k_fwd_gather<<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err); JP_LAUNCH(c);
-		const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
-		cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
-		if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-		JP_TRY(group_step(c, b, cur, pc, false, A, rank_bits, s));
+		// small groups: one fused gather + shared-memory segmented sort; it reports whether any group was too large
+		bool large = force_global;
+		if (!large) {
+			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, sizeof(u32), s));
+			k_seg_sort<<<(A + SG_WIN - 1) / SG_WIN, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
+			                                                                 rank_bits, b.F, b.counters + 2, b.err); JP_LAUNCH(c);
+			JP_KCHECK();
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaStreamSynchronize(s));
+			large = c.h_small[10] != 0;
+		}
+		if (!large) {
+			cur = act;
+			JP_TRY(group_step(c, b, cur, pc, false, true, A, rank_bits, s));
+		} else {
+			// some group spans more than a window: composite-key global radix sort of the whole active set
+			st->ms_phase[5] += 1.0f;                    // counts the rounds that took the global route
+			k_fwd_gather<<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err); JP_LAUNCH(c);
+			const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
+			cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
+			if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+			JP_TRY(group_step(c, b, cur, pc, false, false, A, rank_bits, s));
+		}
 		act = cur ^ 1; pc ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
 		h *= 2; rounds++;

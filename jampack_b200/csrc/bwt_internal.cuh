@@ -45,7 +45,8 @@ template <typename T> inline T* arena_take(Ctx& c, size_t count)
 #define JP_LAUNCH(ctx) (++(ctx).launches)
 #define JP_KCHECK() JP_CUDA(cudaGetLastError())
 
-int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st);
+// scratch_in: nullptr, or d_in itself when the caller allows the input block to be overwritten (keeps the call at 6N)
+int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st, u8* scratch_in);
 int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, jp_bwt_stats* st);
 
 // test hooks

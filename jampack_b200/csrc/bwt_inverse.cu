@@ -270,37 +270,84 @@ __device__ __forceinline__ i32 node_start(u32 id, u32 S, i32 n, int log2m, const
 
 __device__ __forceinline__ u64 pack_rec(u32 next, u32 dist) { return ((u64)next << 32) | dist; }
 
-// Pass 1: per sub-chain (next node, length). Lanes refill independently from a global ticket counter so a
-// warp is not held hostage by its longest (geometrically distributed) sub-chain.
+// ---- work distribution ------------------------------------------------------------------------------
+// Sub-chain lengths are geometric, so lanes finish at different times. A lane that is out of work takes the
+// next node id from its warp's private range; only when the range runs dry does the warp touch the global
+// ticket counter (one atomic per WALK_BATCH sub-chains instead of one per finished sub-chain -- the round trip
+// of that atomic stalls the whole warp).
+constexpr u32 WALK_BATCH = 128;
+struct WarpTickets { u32 next, end; };
+
+__device__ __forceinline__ u32 take_ticket(WarpTickets& wt, bool need, u32* __restrict__ ticket, u32 nodes, bool& done)
+{
+	const u32 nm = __ballot_sync(0xffffffffu, need);
+	if (nm == 0) return REC_INVALID;
+	const u32 cnt = __popc(nm), r = __popc(nm & lanemask_lt()), avail = wt.end - wt.next;
+	u32 my = REC_INVALID;
+	if (need && r < avail) my = wt.next + r;
+	if (cnt > avail) {
+		u32 base = 0;
+		if (lane_id() == 0) base = atomicAdd(ticket, WALK_BATCH);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (need && r >= avail) my = base + (r - avail);
+		wt.next = base + (cnt - avail);
+		wt.end = base + WALK_BATCH;
+	} else wt.next += cnt;
+	if (need && my >= nodes) { done = true; my = REC_INVALID; }
+	return my;
+}
+
+// ---- L2 policies ---------------------------------------------------------------------------------------
+// LF gathers have no reuse (11 % L2 hit rate) and flow through L2 at ~3 TB/s; the output block is written
+// once, in pieces, over the whole launch. Marking the gathers evict-first and the stores evict-last lets a
+// 64 MiB output sit in the 126 MB L2 until its sectors are complete instead of being evicted half-written.
+__device__ __forceinline__ u64 policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 policy_evict_last()  { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u32 ld_lf(const u32* p, u64 pol, bool hinted)
+{
+	u32 v;
+	if (hinted) asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+	else v = __ldg(p);
+	return v;
+}
+__device__ __forceinline__ void st_out16(u8* p, u32 a0, u32 a1, u32 a2, u32 a3, u64 pol, bool hinted)
+{
+	if (hinted) asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "l"(pol) : "memory");
+	else *reinterpret_cast<uint4*>(p) = make_uint4(a0, a1, a2, a3);
+}
+__device__ __forceinline__ void st_out4(u8* p, u32 v, u64 pol, bool hinted)
+{
+	if (hinted) asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+	else *reinterpret_cast<u32*>(p) = v;
+}
+__device__ __forceinline__ void st_out1(u8* p, u32 v, u64 pol, bool hinted)
+{
+	if (hinted) asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+	else *p = (u8)v;
+}
+constexpr int WF_LOAD_EVICT_FIRST = 1, WF_STORE_EVICT_LAST = 2;
+
+// Pass 1: per sub-chain (next node, length).
 __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
                                                               i32 n, int log2m, u32 S, u64* __restrict__ rec,
-                                                              u32* __restrict__ ticket)
+                                                              u32* __restrict__ ticket, int flags)
 {
 	__shared__ AnchorTable anchors;
 	load_anchor_table(anchors, meta);
 	__syncthreads();
 	const i32 idx = meta->idx;
 	const u32 nodes = S + N_ANCHOR;
-	const u32 lane = lane_id(), lt = lanemask_lt();
+	const bool lh = (flags & WF_LOAD_EVICT_FIRST) != 0;
+	const u64 pol_ld = policy_evict_first();
+	WarpTickets wt = {0, 0};
 	u32 id = REC_INVALID, v = 0, len = 0;
 	bool done = false;
 	for (;;) {
-		const bool need = !done && id == REC_INVALID;
-		const u32 nm = __ballot_sync(0xffffffffu, need);
-		if (nm) {
-			const int leader = __ffs(nm) - 1;
-			u32 base = 0;
-			if ((int)lane == leader) base = atomicAdd(ticket, (u32)__popc(nm));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (need) {
-				const u32 my = base + __popc(nm & lt);
-				if (my >= nodes) done = true;
-				else {
-					const i32 bi = node_start(my, S, n, log2m, meta, idx);
-					if (bi < 0) rec[my] = pack_rec(REC_INVALID, 0);
-					else { id = my; len = 0; v = lf[bi]; }
-				}
-			}
+		const u32 my = take_ticket(wt, !done && id == REC_INVALID, ticket, nodes, done);
+		if (my != REC_INVALID) {
+			const i32 bi = node_start(my, S, n, log2m, meta, idx);
+			if (bi < 0) rec[my] = pack_rec(REC_INVALID, 0);
+			else { id = my; len = 0; v = ld_lf(lf + bi, pol_ld, lh); }
 		}
 		if (__ballot_sync(0xffffffffu, !done) == 0) break;
 		if (id != REC_INVALID) {
@@ -309,7 +356,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restr
 			if (r == idx) { rec[id] = pack_rec(S, len); id = REC_INVALID; }
 			else {
 				const i32 bi = row_to_byte(r, idx);
-				v = lf[bi];
+				v = ld_lf(lf + bi, pol_ld, lh);
 				if (v & LF_MARK) { rec[id] = pack_rec(node_of(anchors, r, bi, log2m, S), len); id = REC_INVALID; }
 			}
 		}
@@ -352,44 +399,49 @@ __device__ __forceinline__ u32 symbol_of_row(const i32* __restrict__ C, i32 row)
 	return lo;
 }
 
-// Pass 2: the same walk, now emitting. Bytes are produced right-to-left and packed into a 32-bit
-// accumulator; full words go out as aligned 32-bit stores, the (shared) partial words at either end of a
-// sub-chain as byte stores.
+// cnt (< 16) low bytes of the little-endian 128-bit value a3:a2:a1:a0 to out[pos ..): words where aligned
+__device__ __forceinline__ void store_partial(u8* __restrict__ out, i32 pos, int cnt, u32 a0, u32 a1, u32 a2, u32 a3, u64 pol, bool hinted)
+{
+	int j = 0;
+	while (j < cnt) {
+		if (((pos + j) & 3) == 0 && cnt - j >= 4) { st_out4(out + pos + j, a0, pol, hinted); a0 = a1; a1 = a2; a2 = a3; j += 4; }
+		else {
+			st_out1(out + pos + j, a0 & 255u, pol, hinted);
+			a0 = __funnelshift_r(a0, a1, 8); a1 = __funnelshift_r(a1, a2, 8); a2 = __funnelshift_r(a2, a3, 8); a3 >>= 8;
+			j++;
+		}
+	}
+}
+
+// Pass 2: the same walk, now emitting. Bytes are produced right-to-left and shifted into a 128-bit
+// little-endian accumulator; every completed 16-byte window goes out as one aligned vector store, the
+// partial windows at either end of a sub-chain (shared with the neighbouring sub-chains) as word/byte stores.
 __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
                                                                i32 n, i32 step, int log2m, u32 S, const u64* __restrict__ rec,
                                                                u32* __restrict__ ticket, u8* __restrict__ out,
-                                                               int* __restrict__ err)
+                                                               int* __restrict__ err, int flags)
 {
 	__shared__ i32 C[257];
 	for (int i = threadIdx.x; i < 257; i += blockDim.x) C[i] = meta->ctable[i];
 	__syncthreads();
 	const i32 idx = meta->idx;
 	const u32 nodes = S + N_ANCHOR;
-	const u32 lane = lane_id(), lt = lanemask_lt();
-	u32 id = REC_INVALID, v = 0, acc = 0;
+	const bool lh = (flags & WF_LOAD_EVICT_FIRST) != 0, sh = (flags & WF_STORE_EVICT_LAST) != 0;
+	const u64 pol_ld = policy_evict_first(), pol_st = policy_evict_last();
+	WarpTickets wt = {0, 0};
+	u32 id = REC_INVALID, v = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 	i32 pos = 0, pos_end = 0;
 	bool done = false;
 	for (;;) {
-		const bool need = !done && id == REC_INVALID;
-		const u32 nm = __ballot_sync(0xffffffffu, need);
-		if (nm) {
-			const int leader = __ffs(nm) - 1;
-			u32 base = 0;
-			if ((int)lane == leader) base = atomicAdd(ticket, (u32)__popc(nm));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (need) {
-				const u32 my = base + __popc(nm & lt);
-				if (my >= nodes) done = true;
-				else {
-					const u64 r = rec[my];
-					const u32 nxt = (u32)(r >> 32);
-					const i32 bi = (nxt == REC_INVALID) ? -1 : node_start(my, S, n, log2m, meta, idx);
-					if (bi >= 0) {
-						const i64 pe = (i64)(nxt - S) * step + (u32)r;
-						if (nxt < S || pe > n || pe <= 0) dev_fail(err, DE_CHAIN_RANGE);
-						else { id = my; pos = pos_end = (i32)pe; acc = 0; v = lf[bi]; }
-					}
-				}
+		const u32 my = take_ticket(wt, !done && id == REC_INVALID, ticket, nodes, done);
+		if (my != REC_INVALID) {
+			const u64 r = rec[my];
+			const u32 nxt = (u32)(r >> 32);
+			const i32 bi = (nxt == REC_INVALID) ? -1 : node_start(my, S, n, log2m, meta, idx);
+			if (bi >= 0) {
+				const i64 pe = (i64)(nxt - S) * step + (u32)r;
+				if (nxt < S || pe > n || pe <= 0) dev_fail(err, DE_CHAIN_RANGE);
+				else { id = my; pos = pos_end = (i32)pe; v = ld_lf(lf + bi, pol_ld, lh); }
 			}
 		}
 		if (__ballot_sync(0xffffffffu, !done) == 0) break;
@@ -397,39 +449,41 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 			const i32 r = (i32)(v & LF_MASK);
 			bool stop = (r == idx);
 			if (!stop) {
-				v = lf[row_to_byte(r, idx)];       // next gather goes out before the symbol search below
+				v = ld_lf(lf + row_to_byte(r, idx), pol_ld, lh);   // next gather goes out before the symbol search below
 				stop = (v & LF_MARK) != 0;
 			}
 			const u32 c = symbol_of_row(C, r);
-			if (pos <= 0) { dev_fail(err, DE_CHAIN_RANGE); stop = true; }
+			if (pos <= 0) { dev_fail(err, DE_CHAIN_RANGE); id = REC_INVALID; }
 			else {
 				pos--;
-				acc |= c << ((pos & 3) * 8);
-				if ((pos & 3) == 0) {
-					if (pos + 4 <= pos_end) *reinterpret_cast<u32*>(out + pos) = acc;
-					else for (i32 q = pos; q < pos_end; q++) out[q] = (u8)(acc >> ((q & 3) * 8));
-					acc = 0;
+				a3 = __funnelshift_l(a2, a3, 8); a2 = __funnelshift_l(a1, a2, 8); a1 = __funnelshift_l(a0, a1, 8); a0 = (a0 << 8) | c;
+				if ((pos & 15) == 0) {
+					if (pos + 16 <= pos_end) st_out16(out + pos, a0, a1, a2, a3, pol_st, sh);
+					else store_partial(out, pos, pos_end - pos, a0, a1, a2, a3, pol_st, sh);
+				} else if (stop) {
+					const i32 top = min(pos_end, (pos & ~15) + 16);
+					store_partial(out, pos, top - pos, a0, a1, a2, a3, pol_st, sh);
 				}
-			}
-			if (stop) {
-				if (pos & 3) {
-					const i32 top = min(pos_end, (pos & ~3) + 4);
-					for (i32 q = pos; q < top; q++) out[q] = (u8)(acc >> ((q & 3) * 8));
-				}
-				id = REC_INVALID;
+				if (stop) id = REC_INVALID;
 			}
 		}
 	}
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
+// Marker spacing m. A pass costs about nlen / (gather rate) + (longest sub-chain) * (unloaded DRAM latency), and
+// the longest of nlen/m geometric sub-chains is ~ m * ln(nlen/m): measured on 64 MiB, m = 64 / 32 / 16 give
+// 1.46 / 1.29 / 1.19 ms for pass 1. Smaller m means more 8-byte records (8 * nlen / m bytes) and more ranking work.
 static int pick_log2m(i32 nlen)
 {
-	int lg = 6;
 	if (const char* e = getenv("JP_BWT_INV_LOG2M")) { int v = atoi(e); if (v >= 2 && v <= 12) return v; }
-	// aim for >= 2^19 sub-chains, spacing between 8 and 64 rows
-	while (lg > 3 && ((i64)nlen >> lg) < (1 << 19)) lg--;
-	return lg;
+	return nlen >= (1 << 22) ? 4 : 3;
+}
+
+static int walk_flags()
+{
+	if (const char* e = getenv("JP_BWT_INV_FLAGS")) return atoi(e);
+	return 0;   // measured on B200: the L2 policies change nothing (3.73 ms without, 3.82-3.91 ms with)
 }
 
 static int walker_blocks(Ctx& c, const void* kernel)
@@ -444,20 +498,23 @@ struct InvBuffers {
 	int tiles; int log2m; u32 S;
 };
 
-static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b)
+// `scratch_in`: when the caller's input block may be overwritten once the LF table is built, the sub-chain
+// records live there (8 * nodes <= nlen bytes) and the workspace is lf + per-tile histograms: 6N + N/64 in all.
+static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr)
 {
 	b.tiles = (int)(((i64)nlen + INV_TILE - 1) / INV_TILE);
 	b.log2m = pick_log2m(nlen);
 	b.S = (u32)(((i64)nlen + (1 << b.log2m) - 1) >> b.log2m);
 	const size_t nodes = (size_t)b.S + N_ANCHOR;
+	const bool rec_in_input = scratch_in != nullptr && nodes * 8 <= (size_t)nlen && ((uintptr_t)scratch_in & 7) == 0;
 	size_t total = Arena::align((size_t)nlen * 4) + Arena::align((size_t)b.tiles * 256 * 4) + Arena::align(256 * 4) +
-	               Arena::align(sizeof(InvMeta)) + Arena::align(nodes * 8) + Arena::align(64) + Arena::align(64);
+	               Arena::align(sizeof(InvMeta)) + (rec_in_input ? 0 : Arena::align(nodes * 8)) + Arena::align(64) + Arena::align(64);
 	JP_TRY(arena_reserve(c, total));
 	b.lf = arena_take<u32>(c, (size_t)nlen);
 	b.tile_hist = arena_take<u32>(c, (size_t)b.tiles * 256);
 	b.bin_total = arena_take<u32>(c, 256);
 	b.meta = arena_take<InvMeta>(c, 1);
-	b.rec = arena_take<u64>(c, nodes);
+	b.rec = rec_in_input ? reinterpret_cast<u64*>(scratch_in) : arena_take<u64>(c, nodes);
 	b.ticket = arena_take<u32>(c, 16);
 	b.err = arena_take<int>(c, 16);
 	return JP_OK;
@@ -475,7 +532,7 @@ static int inv_build_table(Ctx& c, const u8* d_in, i32 len, i32 nlen, u8* d_out,
 	return JP_OK;
 }
 
-int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st)
+int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st, u8* scratch_in)
 {
 	const i32 len = len_with_trailer - JP_BWT_TRAILER_BYTES;            // bwt.cpp:77
 	if (len < 0) return JP_ERR_ARG;
@@ -491,7 +548,7 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	}
 	const i32 step = nlen / JP_BWT_UNITS;                               // bwt.cpp:176 with N_Units = 120
 	InvBuffers b;
-	JP_TRY(inv_alloc(c, nlen, b));
+	JP_TRY(inv_alloc(c, nlen, b, scratch_in));
 	JP_TRY(inv_build_table(c, d_in, len, nlen, d_out, b, s));
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
@@ -500,14 +557,14 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
 	const u32 nodes = b.S + N_ANCHOR;
 	const int wb1 = walker_blocks(c, (const void*)k_inv_walk_len);
-	k_inv_walk_len<<<wb1, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket); JP_LAUNCH(c);
+	k_inv_walk_len<<<wb1, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, walk_flags()); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[4], s));
 	const int wb2 = walker_blocks(c, (const void*)k_inv_walk_emit);
-	k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err); JP_LAUNCH(c);
+	k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err, walk_flags()); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[5], s));
 	JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));

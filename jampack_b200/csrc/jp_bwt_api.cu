@@ -182,7 +182,7 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	if (in_bytes) JP_CUDA(cudaMemcpyAsync(c.d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
 	JP_CUDA(cudaEventRecord(c.ev[9], s));
 	int rc = direction == 0 ? forward_device(c, c.d_in, len, c.d_out, s, &t_stats)
-	                        : inverse_device(c, c.d_in, in_len, c.d_out, s, &t_stats);
+	                        : inverse_device(c, c.d_in, in_len, c.d_out, s, &t_stats, c.d_in);   // our own copy: free scratch
 	if (rc != JP_OK) return rc;
 	JP_CUDA(cudaEventRecord(c.ev[10], s));
 	if (out_bytes) JP_CUDA(cudaMemcpyAsync(out, c.d_out, out_bytes, cudaMemcpyDeviceToHost, s));
@@ -195,7 +195,7 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	return JP_OK;
 }
 
-static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int device, void* stream)
+static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int device, void* stream, bool consume_in = false)
 {
 	if (!d_in || !d_out || in_len < 0 || device < 0) { set_error_detail("null pointer, negative length or device"); return JP_ERR_ARG; }
 	if (direction == 1 && in_len < JP_BWT_TRAILER_BYTES) { set_error_detail("inverse input shorter than its trailer"); return JP_ERR_ARG; }
@@ -206,7 +206,7 @@ static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int
 	begin_call(c);
 	cudaStream_t s = stream ? (cudaStream_t)stream : c.own_stream;
 	int rc = direction == 0 ? forward_device(c, d_in, in_len, d_out, s, &t_stats)
-	                        : inverse_device(c, d_in, in_len, d_out, s, &t_stats);
+	                        : inverse_device(c, d_in, in_len, d_out, s, &t_stats, consume_in ? const_cast<u8*>(d_in) : nullptr);
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high;
 	return rc;
@@ -222,6 +222,7 @@ int jp_bwt_forward(const uint8_t* in, int32_t len, uint8_t* out, int32_t* out_le
 int jp_bwt_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, int32_t* out_len) { return host_call(1, in, len_with_trailer, out, out_len); }
 int jp_bwt_forward_device(const uint8_t* d_in, int32_t len, uint8_t* d_out, int device, void* stream) { return device_call(0, d_in, len, d_out, device, stream); }
 int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream) { return device_call(1, d_in, len_with_trailer, d_out, device, stream); }
+int jp_bwt_inverse_device_consume(uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream) { return device_call(1, d_in, len_with_trailer, d_out, device, stream, true); }
 
 int jp_bwt_set_devices(const int* ids, int n)
 {

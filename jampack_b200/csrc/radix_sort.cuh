@@ -19,8 +19,12 @@ constexpr size_t RS_SMEM_SCATTER = (size_t)RS_TILE * (8 + 4);
 
 __device__ __forceinline__ u32 rs_digit(u64 k, int shift) { return (u32)(k >> shift) & 255u; }
 
-// tile_hist[tile][digit]
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ tile_hist)
+// Histogram layout is digit-major, tile_hist[digit * stride + tile] (stride = tiles rounded up to 4), so that
+// the per-digit scan over tiles reads and writes whole rows (the tile-major layout made that scan as
+// expensive as the scatter itself: 0.31 ms per pass at 16 K tiles, ncu round 1).
+__host__ __device__ __forceinline__ u32 rs_stride(u32 tiles) { return (tiles + 3u) & ~3u; }
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ tile_hist, u32 stride)
 {
 	__shared__ u32 h[RS_WARPS][256];
 	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -40,48 +44,51 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ 
 	u32 s = 0;
 	#pragma unroll
 	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
-	tile_hist[(size_t)blockIdx.x * 256 + t] = s;
+	tile_hist[(size_t)t * stride + blockIdx.x] = s;
 }
 
-// block d: total of digit d over all tiles
-__global__ void __launch_bounds__(256) k_rs_totals(const u32* __restrict__ tile_hist, int tiles, u32* __restrict__ totals)
+// block d: total of digit d over all tiles (one coalesced row)
+__global__ void __launch_bounds__(256) k_rs_totals(const u32* __restrict__ tile_hist, u32 tiles, u32 stride, u32* __restrict__ totals)
 {
 	__shared__ u32 ws[32];
-	const int d = blockIdx.x, t = threadIdx.x;
+	const u32 d = blockIdx.x, t = threadIdx.x;
+	const u32* row = tile_hist + (size_t)d * stride;
 	u32 s = 0;
-	for (int k = t; k < tiles; k += 256) s += tile_hist[(size_t)k * 256 + d];
+	for (u32 k = t; k < tiles; k += 256) s += row[k];
 	u32 total;
 	block_incl_sum(s, ws, &total);
 	if (t == 0) totals[d] = total;
 }
 
-// block d: tile_hist[.][d] <- global offset of tile's first key with digit d
-__global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, int tiles, const u32* __restrict__ totals)
+// block d: row d <- global offset of each tile's first key with digit d (exclusive scan + digit base)
+__global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u32 tiles, u32 stride, const u32* __restrict__ totals)
 {
 	__shared__ u32 ws[32];
-	const int d = blockIdx.x, t = threadIdx.x;
-	u32 total;
-	const u32 below = block_incl_sum(t < d ? totals[t] : 0u, ws, &total);
-	(void)below;
-	const u32 digit_base = total;                         // sum of totals[0..d)
-	const int per = (tiles + 255) / 256;
-	const int lo = min(tiles, t * per), hi = min(tiles, lo + per);
-	u32 s = 0;
-	for (int k = lo; k < hi; k++) s += tile_hist[(size_t)k * 256 + d];
-	u32 tt;
-	const u32 inc = block_incl_sum(s, ws, &tt);
-	u32 run = digit_base + inc - s;
-	for (int k = lo; k < hi; k++) {
-		const size_t a = (size_t)k * 256 + d;
-		const u32 v = tile_hist[a];
-		tile_hist[a] = run;
-		run += v;
+	const u32 d = blockIdx.x, t = threadIdx.x;
+	u32 carry;
+	block_incl_sum(t < d ? totals[t] : 0u, ws, &carry);    // carry = sum of totals[0..d)
+	u32* row = tile_hist + (size_t)d * stride;
+	for (u32 base = 0; base < tiles; base += 1024) {
+		const u32 k = base + t * 4;
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (k < tiles) v = *reinterpret_cast<const uint4*>(row + k);   // rows are padded to a multiple of 4 entries
+		if (k + 1 >= tiles) v.y = 0;
+		if (k + 2 >= tiles) v.z = 0;
+		if (k + 3 >= tiles) v.w = 0;
+		const u32 sum = v.x + v.y + v.z + v.w;
+		u32 total;
+		const u32 inc = block_incl_sum(sum, ws, &total);
+		u32 run = carry + inc - sum;
+		uint4 o;
+		o.x = run; run += v.x; o.y = run; run += v.y; o.z = run; run += v.z; o.w = run;
+		if (k < tiles) *reinterpret_cast<uint4*>(row + k) = o;
+		carry += total;
 	}
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin,
                                                            u64* __restrict__ kout, u32* __restrict__ vout,
-                                                           const u32* __restrict__ tile_off, u32 n, int shift)
+                                                           const u32* __restrict__ tile_off, u32 stride, u32 n, int shift)
 {
 	extern __shared__ __align__(16) u8 rs_smem[];
 	u64* skey = reinterpret_cast<u64*>(rs_smem);
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict
 	u32 total;
 	const u32 inc = block_incl_sum(run, ws, &total);
 	bin_start[t] = inc - run;
-	g_off[t] = tile_off[(size_t)blockIdx.x * 256 + t] - (inc - run);
+	g_off[t] = tile_off[(size_t)t * stride + blockIdx.x] - (inc - run);
 	__syncthreads();
 
 	#pragma unroll
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict
 
 struct RadixBuffers {
 	u64* k[2]; u32* v[2];
-	u32* tile_hist;   // ceil(n / RS_TILE) * 256
+	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries
 	u32* totals;      // 256
 };
 
@@ -166,12 +173,12 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 	if (n == 0) return cur;
 	// function attributes are per device; setting one is a host-only call
 	if (cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
-	const int tiles = (int)radix_tiles(n);
+	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		k_rs_hist<<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist);
-		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, b.totals);
-		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, b.totals);
-		k_rs_scatter<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, n, shift);
+		k_rs_hist<<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride);
+		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
+		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
+		k_rs_scatter<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift);
 		*launches += 4;
 		cur ^= 1;
 	}
