@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 // ---- 4/5. group heads -> ranks, retire singletons, compact the rest ----------------------------------
 // Scan element: (P of the last group head so far, #survivors, #surviving group heads).
 constexpr int GS_THREADS = 256;
-constexpr int GS_SUB     = 16;
+constexpr int GS_SUB     = 8;
 constexpr int GS_TILE    = GS_THREADS * GS_SUB;
 struct GAgg { i32 mh; u32 ns; u32 ng; u32 pad; };
 
@@ -177,55 +177,85 @@ __global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg,
 	if (t == 1023) { out[0] = pns + ins; out[1] = png + ing; }
 }
 
+// All GS_SUB sub-tiles of a tile are loaded up front (GS_SUB independent loads per array in flight), scanned
+// inside each warp, and stitched together with ONE barrier through a [sub-tile][warp] table -- the earlier
+// one-sub-tile-at-a-time version exposed a full load latency and two barriers per 256 elements (ncu: 93
+// long-scoreboard + 50 barrier stall cycles per issue).
 __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict__ K, const u8* __restrict__ F, const u32* __restrict__ V,
                                                           const u32* __restrict__ P, u32 A, const GAgg* __restrict__ agg,
-                                                          int rank_bits, u32* __restrict__ ISA, u32* __restrict__ SA,
+                                                          int rank_bits, u32* __restrict__ ISA, u32* __restrict__ R, u32* __restrict__ SA,
                                                           u64* __restrict__ Kn, u32* __restrict__ Vn, u32* __restrict__ Pn)
 {
-	__shared__ i32 wmh[8];
-	__shared__ u32 wcnt[8];
+	__shared__ i32 wmh[GS_SUB][8];
+	__shared__ u32 wpk[GS_SUB][8];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const u32 base = blockIdx.x * GS_TILE;
 	const GAgg carry0 = agg[blockIdx.x];
-	i32 cmh = carry0.mh; u32 cns = carry0.ns, cng = carry0.ng;
+
+	u32 v[GS_SUB], p[GS_SUB], fl[GS_SUB];     // fl: bit0 valid, bit1 head, bit2 survivor, bit3 surviving head
+	#pragma unroll
 	for (int s = 0; s < GS_SUB; s++) {
 		const u32 j = base + s * GS_THREADS + t;
-		if (base + s * GS_THREADS >= A) break;          // uniform across the block
-		bool head = false, surv = false, shead = false;
-		u32 v = 0, p = 0;
+		v[s] = 0; p[s] = 0; fl[s] = 0;
 		if (j < A) {
 			const GFlags f = group_flags(K, F, j, A);
-			head = f.head; surv = !(f.head && f.nhead); shead = f.head && !f.nhead;
-			v = V[j]; p = P ? P[j] : j;
+			fl[s] = 1u | (f.head ? 2u : 0u) | (!(f.head && f.nhead) ? 4u : 0u) | ((f.head && !f.nhead) ? 8u : 0u);
+			v[s] = V[j]; p[s] = P ? P[j] : j;
 		}
-		const i32 mh = head ? (i32)p : -1;
-		const u32 packed = (surv ? 1u : 0u) | (shead ? 0x10000u : 0u);
-		i32 imh = warp_incl_max(mh);
-		u32 ipk = warp_incl_sum(packed);
-		if (lane == 31) { wmh[w] = imh; wcnt[w] = ipk; }
-		__syncthreads();
-		i32 pmh = cmh; u32 ppk = 0, tpk = 0;
-		i32 tmh = cmh;
+	}
+	i32 imh[GS_SUB]; u32 ipk[GS_SUB];
+	#pragma unroll
+	for (int s = 0; s < GS_SUB; s++) {
+		const i32 mh = (fl[s] & 2u) ? (i32)p[s] : -1;
+		const u32 packed = ((fl[s] >> 2) & 1u) | (((fl[s] >> 3) & 1u) << 16);
+		imh[s] = warp_incl_max(mh);
+		ipk[s] = warp_incl_sum(packed);
+		if (lane == 31) { wmh[s][w] = imh[s]; wpk[s][w] = ipk[s]; }
+	}
+	__syncthreads();
+	i32 run_mh = carry0.mh; u32 run_pk = 0;
+	#pragma unroll
+	for (int s = 0; s < GS_SUB; s++) {
+		i32 pm = run_mh, tm = run_mh; u32 pp = run_pk, tp = run_pk;
 		#pragma unroll
 		for (int k = 0; k < 8; k++) {
-			const i32 a = wmh[k]; const u32 b = wcnt[k];
-			if (k < w) { pmh = max(pmh, a); ppk += b; }
-			tmh = max(tmh, a); tpk += b;
+			const i32 a = wmh[s][k]; const u32 b = wpk[s][k];
+			if (k < w) { pm = max(pm, a); pp += b; }
+			tm = max(tm, a); tp += b;
 		}
-		imh = max(imh, pmh);
-		ipk += ppk;
-		if (j < A) {
-			const u32 ns_incl = cns + (ipk & 0xffffu);
-			const u32 ng_incl = cng + (ipk >> 16);
-			ISA[v] = (u32)imh + 1u;
-			if (surv) {
-				const u32 q = ns_incl - 1;
-				Vn[q] = v; Pn[q] = p; Kn[q] = (u64)(ng_incl - 1) << rank_bits;
-			} else SA[p] = v;
+		if (fl[s] & 1u) {
+			const i32 fmh = max(imh[s], pm);
+			const u32 fpk = ipk[s] + pp;
+			if (R) R[base + s * GS_THREADS + t] = (u32)fmh + 1u;   // ranks leave in slot order; k_isa_scatter places them
+			else ISA[v[s]] = (u32)fmh + 1u;
+			if (fl[s] & 4u) {
+				const u32 q = carry0.ns + (fpk & 0xffffu) - 1;
+				Vn[q] = v[s]; Pn[q] = p[s]; Kn[q] = (u64)(carry0.ng + (fpk >> 16) - 1) << rank_bits;
+			} else SA[p[s]] = v[s];
 		}
-		cmh = tmh; cns += tpk & 0xffffu; cng += tpk >> 16;
-		__syncthreads();
+		run_mh = tm; run_pk = tp;
 	}
+}
+
+// ISA[V[j]] = R[j] is a random 4-byte scatter; done naively every store dirties one sector that DRAM later has to
+// read-modify-write (ncu: 2.7 ms for 64 M ranks, 24 G stores/s against 72 G/s for gathers). Instead the slots are
+// streamed once per REGION of ISA (2^region_log2 entries, sized to stay L2-resident): a pass only stores the ranks
+// that fall in its region, so the sectors fill up in L2 and go to DRAM once, complete. Blocks are ordered by
+// region, so the passes follow each other inside one launch.
+__global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, const u32* __restrict__ R, u32 A, u32* __restrict__ ISA,
+                                                     int region_log2, u32 tiles)
+{
+	const u32 region = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+	const u32 base = tile * 2048 + threadIdx.x;
+	u32 v[8], r[8];
+	#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const u32 j = base + i * 256;
+		v[i] = 0xffffffffu; r[i] = 0;
+		if (j < A) { v[i] = __ldcs(V + j); r[i] = __ldcs(R + j); }
+	}
+	#pragma unroll
+	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (v[i] >> region_log2) == region) ISA[v[i]] = r[i];
 }
 
 // ---- 5a. doubling round, small groups: gather + segmented sort in shared memory -------------------------
@@ -240,36 +270,31 @@ constexpr int SG_ITEMS   = 16;
 constexpr int SG_CAP     = SG_THREADS * SG_ITEMS;   // 4096 elements sorted per block
 constexpr int SG_WIN     = SG_CAP / 2;              // window of group heads per block
 constexpr size_t SG_SMEM = (size_t)SG_CAP * (8 + 4);
+constexpr u32 SG_PAIR_MAX = 256;                    // longest group the all-pairs rank refinement takes on
 
-__global__ void __launch_bounds__(SG_THREADS) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
-                                                         const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
-                                                         u8* __restrict__ F, u32* __restrict__ has_large, int* __restrict__ err)
+struct SegTile { u32 start, len; };
+
+// Slot range [start, start+len) of the groups whose head lies in window `win` (len == 0: nothing to do).
+__device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K, u32 A, int rank_bits,
+                                             u32* __restrict__ sh /*[3]*/, u32* __restrict__ has_large)
 {
-	extern __shared__ __align__(16) u8 sg_smem[];
-	u64* skey = reinterpret_cast<u64*>(sg_smem);
-	u32* sval = reinterpret_cast<u32*>(sg_smem + (size_t)SG_CAP * 8);
-	__shared__ u32 wcnt[SG_THREADS / 32][256];
-	__shared__ u32 bin_start[256];
-	__shared__ u32 ws[32];
-	__shared__ u32 s_first, s_lasthead, s_end;
-
-	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-	const u32 lt = lanemask_lt();
-	const u32 w0 = blockIdx.x * SG_WIN;
+	const int t = threadIdx.x;
+	const u32 w0 = win * SG_WIN;
 	const u32 L = min(w0 + (u32)SG_WIN, A);
-	if (t == 0) { s_first = 0xffffffffu; s_lasthead = 0; s_end = 0xffffffffu; }
+	SegTile r; r.start = 0; r.len = 0;
+	if (t == 0) { sh[0] = 0xffffffffu; sh[1] = 0; sh[2] = 0xffffffffu; }
 	__syncthreads();
 	#pragma unroll
 	for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
 		const u32 j = w0 + i * SG_THREADS + t;
 		if (j < L) {
 			const u64 g = K[j] >> rank_bits;
-			if (j == 0 || (K[j - 1] >> rank_bits) != g) { atomicMin(&s_first, j); atomicMax(&s_lasthead, j); }
+			if (j == 0 || (K[j - 1] >> rank_bits) != g) { atomicMin(&sh[0], j); atomicMax(&sh[1], j); }
 		}
 	}
 	__syncthreads();
-	const u32 start = s_first;
-	if (start == 0xffffffffu) return;                 // the window lies inside a group owned by an earlier block
+	const u32 start = sh[0];
+	if (start == 0xffffffffu) return r;               // the window lies inside a group owned by an earlier block
 	u32 end;
 	if (L == A) end = A;
 	else {
@@ -278,36 +303,173 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_sort(const u64* __restrict__
 		#pragma unroll
 		for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
 			const u32 j = L + i * SG_THREADS + t;
-			if (j < lim && (K[j] >> rank_bits) != gl) atomicMin(&s_end, j);
+			if (j < lim && (K[j] >> rank_bits) != gl) atomicMin(&sh[2], j);
 		}
 		__syncthreads();
-		end = s_end;
+		end = sh[2];
 		if (end == 0xffffffffu) {
 			if (lim == A) end = A;
-			else { end = s_lasthead; if (t == 0) *has_large = 1u; }   // last group spans > a window: not ours
+			else { end = sh[1]; if (t == 0 && has_large) *has_large = 1u; }   // last group spans > a window: not ours
 		}
 	}
-	if (end <= start) return;
-	const u32 len = end - start;                      // <= SG_CAP by construction
-	const u64 g0 = K[start] >> rank_bits;
-	const u32 gmax = (u32)((K[end - 1] >> rank_bits) - g0);
-	const int bits = rank_bits + bit_length((u64)gmax);
+	if (end <= start) return r;
+	r.start = start; r.len = end - start;             // <= SG_CAP by construction
+	return r;
+}
 
+__device__ __forceinline__ u32 warp_rev_incl_min(u32 v)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(0xffffffffu, v, o); if (lane_id() + o < 32) v = min(v, t); }
+	return v;
+}
+
+// Light kernel: tiles whose groups are all short are finished here by warp-level rank refinement; the others
+// are queued for k_seg_sort_radix. Every element learns its group's slot range [gs, ge) from two warp-level
+// scans (last head at or before me / first group end at or after me) stitched across the block through a small
+// table with a single barrier; then it counts the members of its group that sort before it.
+constexpr size_t SG_SMEM_LIGHT = (size_t)SG_CAP * (4 + 4 + 1);
+__global__ void __launch_bounds__(SG_THREADS, 4) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
+                                                         const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+                                                         u8* __restrict__ F, u32* __restrict__ counters /*[2]=has_large [3]=queued*/,
+                                                         u32* __restrict__ queue, int* __restrict__ err)
+{
+	extern __shared__ __align__(16) u8 sg_smem[];
+	u32* skey = reinterpret_cast<u32*>(sg_smem);        // key2 = ISA[s + h]; later the refined suffix ids
+	u32* sval = skey + SG_CAP;                          // suffix ids in slot order
+	u8* sflag = reinterpret_cast<u8*>(sval + SG_CAP);   // head flags of the refined order
+	__shared__ u32 sh[3];
+	__shared__ u32 wf[SG_ITEMS][SG_THREADS / 32], wb[SG_ITEMS][SG_THREADS / 32];
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const SegTile tile = seg_range(blockIdx.x, K, A, rank_bits, sh, counters + 2);
+	const u32 len = tile.len, start = tile.start;
+	if (len == 0) return;
+
+	// per element, packed: bits 0-12 last head at or before me (-> group start), bits 13-25 first group end at or
+	// after me, bit 26 head, bit 27 last of its group, bit 28 valid
+	u32 pk[SG_ITEMS];
+	#pragma unroll 4
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = i * SG_THREADS + t;
+		u32 hl = 0;
+		if (e < len) {
+			const u32 j = start + e;
+			const u32 v = V[j];
+			const u64 g = K[j] >> rank_bits;
+			const bool head = (e == 0) || (K[j - 1] >> rank_bits) != g;
+			const bool last = (e == len - 1) || (K[j + 1] >> rank_bits) != g;
+			u32 p = v + h;
+			if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+			sval[e] = v;
+			skey[e] = __ldg(&ISA[p]);
+			hl = (head ? 1u : 0u) | (last ? 2u : 0u) | 4u;
+		}
+		const u32 f = warp_incl_max((hl & 1u) ? (i32)e : 0);
+		const u32 b = warp_rev_incl_min((hl & 2u) ? e + 1 : 0x1fffu);
+		if (lane == 31) wf[i][w] = f;
+		if (lane == 0) wb[i][w] = b;
+		pk[i] = f | (b << 13) | (hl << 26);
+	}
+	__syncthreads();
+	int big = 0;
+	{
+		u32 run = 0;
+		#pragma unroll
+		for (int i = 0; i < SG_ITEMS; i++) {
+			u32 pm = run, tm = run;
+			#pragma unroll
+			for (int k = 0; k < SG_THREADS / 32; k++) { const u32 a = wf[i][k]; if (k < w) pm = max(pm, a); tm = max(tm, a); }
+			pk[i] = (pk[i] & ~0x1fffu) | max(pk[i] & 0x1fffu, pm);
+			run = tm;
+		}
+		run = 0x1fffu;
+		#pragma unroll
+		for (int i = SG_ITEMS - 1; i >= 0; i--) {
+			u32 pm = run, tm = run;
+			#pragma unroll
+			for (int k = SG_THREADS / 32 - 1; k >= 0; k--) { const u32 a = wb[i][k]; if (k > w) pm = min(pm, a); tm = min(tm, a); }
+			const u32 ge = min((pk[i] >> 13) & 0x1fffu, pm);
+			pk[i] = (pk[i] & ~(0x1fffu << 13)) | (ge << 13);
+			if ((pk[i] >> 28) & 1u) big |= (ge - (pk[i] & 0x1fffu) > SG_PAIR_MAX);
+			run = tm;
+		}
+	}
+	if (__syncthreads_or(big)) {                        // a long group: the radix kernel takes this tile
+		if (t == 0) queue[atomicAdd(counters + 3, 1u)] = blockIdx.x;
+		return;
+	}
+	// ---- warp-level rank refinement: new slot = group start + #smaller + #equal-and-earlier (stable); an
+	// element opens a new sub-group iff no equal key precedes it. Groups here hold a few to a few dozen suffixes.
+	#pragma unroll 2
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = i * SG_THREADS + t;
+		if ((pk[i] >> 28) & 1u) {
+			const u32 mine = skey[e];
+			const u32 gs = pk[i] & 0x1fffu, ge = (pk[i] >> 13) & 0x1fffu;
+			u32 cnt = 0, eqb = 0;
+			for (u32 k = gs; k < e; k++) { const u32 o = skey[k]; cnt += (o <= mine); eqb += (o == mine); }
+			for (u32 k = e + 1; k < ge; k++) cnt += (skey[k] < mine);
+			pk[i] = (gs + cnt) | (eqb == 0 ? 0x10000u : 0u) | (1u << 28);
+		}
+	}
+	__syncthreads();                                    // every key2 has been read: skey becomes the output staging
+	#pragma unroll
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = i * SG_THREADS + t;
+		if ((pk[i] >> 28) & 1u) { const u32 pos = pk[i] & 0xffffu; skey[pos] = sval[e]; sflag[pos] = (u8)((pk[i] >> 16) & 1u); }
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = i * SG_THREADS + t;
+		if (e < len) { V[start + e] = skey[e]; F[start + e] = sflag[e]; }
+	}
+}
+
+// Radix route for the queued tiles: LSD radix sort of (local group id, key2) that never leaves shared memory.
+__global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
+                                                               const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+                                                               u8* __restrict__ F, const u32* __restrict__ queue, int* __restrict__ err)
+{
+	extern __shared__ __align__(16) u8 sg_smem[];
+	u64* skey = reinterpret_cast<u64*>(sg_smem);
+	u32* sval = reinterpret_cast<u32*>(sg_smem + (size_t)SG_CAP * 8);
+	__shared__ u32 wcnt[SG_THREADS / 32][256];
+	__shared__ u32 bin_start[256];
+	__shared__ u32 ws[32];
+	__shared__ u32 sh[3];
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	const u32 lt = lanemask_lt();
+	const SegTile tile = seg_range(queue[blockIdx.x], K, A, rank_bits, sh, nullptr);
+	const u32 len = tile.len, start = tile.start;
+	if (len == 0) return;
+	{
+		const u64 g0 = K[start] >> rank_bits;
+		#pragma unroll 4
+		for (int i = 0; i < SG_ITEMS; i++) {
+			const u32 e = i * SG_THREADS + t;
+			if (e < len) {
+				const u32 j = start + e;
+				const u32 v = V[j];
+				u32 p = v + h;
+				if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+				sval[e] = v;
+				skey[e] = (((K[j] >> rank_bits) - g0) << 32) | (u64)__ldg(&ISA[p]);
+			}
+		}
+		__syncthreads();
+	}
+	const u32 gmax = (u32)(skey[len - 1] >> 32);
+	const int bits = rank_bits + bit_length((u64)gmax);
 	u64 key[SG_ITEMS];
 	u32 val[SG_ITEMS];
 	#pragma unroll
 	for (int i = 0; i < SG_ITEMS; i++) {
 		const u32 e = w * (32 * SG_ITEMS) + i * 32 + lane;
 		key[i] = ~0ull; val[i] = 0;
-		if (e < len) {
-			const u32 j = start + e;
-			const u32 v = V[j];
-			u32 p = v + h;
-			if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
-			val[i] = v;
-			key[i] = (((K[j] >> rank_bits) - g0) << rank_bits) | (u64)__ldg(&ISA[p]);
-		}
+		if (e < len) { const u64 c = skey[e]; key[i] = ((c >> 32) << rank_bits) | (c & 0xffffffffull); val[i] = sval[e]; }
 	}
+	__syncthreads();
 
 	for (int shift = 0; shift < bits; shift += 8) {
 		for (int i = t; i < (SG_THREADS / 32) * 256; i += SG_THREADS) (&wcnt[0][0])[i] = 0;
@@ -412,8 +574,10 @@ __global__ void k_fwd_trailer(const u8* __restrict__ T, const u32* __restrict__ 
 struct FwdBuffers {
 	RadixBuffers rb;
 	u32* P[2];
-	u32* ISA; u32* SA;
+	u32* ISA; u32* SA; u32* R;
+	int isa_region_log2;
 	u8* F;
+	u32* queue;
 	GAgg* agg;
 	FwdMeta* meta;
 	u32* counters;
@@ -424,17 +588,20 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 {
 	const size_t N = (size_t)n;
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
-	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + Arena::align(N * 4) +
+	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + 2 * Arena::align(N * 4) +
 	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align(gtiles * sizeof(GAgg)) +
-	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16);
+	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + Arena::align((N / SG_WIN + 16) * 4);
 	JP_TRY(arena_reserve(c, total));
 	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
 	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
 	b.P[0] = arena_take<u32>(c, N); b.P[1] = arena_take<u32>(c, N);
-	b.ISA = arena_take<u32>(c, N + 1); b.SA = arena_take<u32>(c, N);
+	b.ISA = arena_take<u32>(c, N + 1); b.SA = arena_take<u32>(c, N); b.R = arena_take<u32>(c, N);
+	b.isa_region_log2 = 24;                            // 2^24 ranks = 64 MiB of ISA per pass (measured best of 2^21..2^25)
+	if (const char* e = getenv("JP_BWT_ISA_REGION_LOG2")) b.isa_region_log2 = atoi(e);
 	b.rb.tile_hist = arena_take<u32>(c, (rtiles + 4) * 256);
 	b.rb.totals = arena_take<u32>(c, 256);
 	b.F = arena_take<u8>(c, N + 16);
+	b.queue = arena_take<u32>(c, N / SG_WIN + 16);
 	b.agg = arena_take<GAgg>(c, gtiles);
 	b.meta = arena_take<FwdMeta>(c, 1);
 	b.counters = arena_take<u32>(c, 16);
@@ -450,8 +617,15 @@ static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos,
 	const u8* F = use_flags ? b.F : nullptr;
 	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, P, A, b.agg); JP_LAUNCH(c);
 	k_grp_scan_tiles<<<1, 1024, 0, s>>>(b.agg, tiles, b.counters); JP_LAUNCH(c);
-	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, b.SA,
+	// small active sets (and the A/B switch region_log2 <= 0) scatter straight from the apply kernel
+	const bool staged = b.isa_region_log2 > 0 && A > (1u << 20);
+	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, staged ? b.R : nullptr, b.SA,
 	                                          b.rb.k[cur ^ 1], b.rb.v[cur ^ 1], b.P[pc ^ 1]); JP_LAUNCH(c);
+	if (staged) {
+		const u32 n_entries = c.cur_n + 1, regions = (n_entries + (1u << b.isa_region_log2) - 1) >> b.isa_region_log2;
+		const u32 stiles = (A + 2047) / 2048;
+		k_isa_scatter<<<regions * stiles, 256, 0, s>>>(b.rb.v[cur], b.R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
+	}
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 8, b.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -462,6 +636,7 @@ static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos,
 // Builds SA and ISA (ranks 1..n; ISA[n] = 0) of T[0..n) in b. Events ev[1..4] mark the phase boundaries.
 static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t s, jp_bwt_stats* st)
 {
+	c.cur_n = (u32)n;
 	JP_CUDA(cudaMemsetAsync(b.meta, 0, sizeof(FwdMeta), s));
 	JP_CUDA(cudaMemsetAsync(b.err, 0, 64, s));
 	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
@@ -480,7 +655,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
-	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
+	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
 	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, bits * depth, s, &c.launches);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
@@ -503,13 +679,20 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		// small groups: one fused gather + shared-memory segmented sort; it reports whether any group was too large
 		bool large = force_global;
 		if (!large) {
-			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, sizeof(u32), s));
-			k_seg_sort<<<(A + SG_WIN - 1) / SG_WIN, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
-			                                                                 rank_bits, b.F, b.counters + 2, b.err); JP_LAUNCH(c);
+			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 2 * sizeof(u32), s));
+			k_seg_sort<<<(A + SG_WIN - 1) / SG_WIN, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
+			                                                                 rank_bits, b.F, b.counters, b.queue, b.err); JP_LAUNCH(c);
 			JP_KCHECK();
-			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 			JP_CUDA(cudaStreamSynchronize(s));
 			large = c.h_small[10] != 0;
+			const u32 queued = (u32)c.h_small[11];
+			if (!large && queued) {
+				k_seg_sort_radix<<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
+				                                                    rank_bits, b.F, b.queue, b.err); JP_LAUNCH(c);
+				JP_KCHECK();
+				st->ms_phase[6] += (float)queued;       // tiles that needed the shared-memory radix route
+			}
 		}
 		if (!large) {
 			cur = act;
@@ -567,7 +750,7 @@ int debug_suffix_array(Ctx& c, const u8* h_in, i32 n, i32* h_sa)
 	c.arena.reset();
 	FwdBuffers b;
 	const size_t N = (size_t)n;
-	JP_TRY(arena_reserve(c, N * 48 + (8u << 20)));
+	JP_TRY(arena_reserve(c, N * 56 + (8u << 20)));
 	u8* d_T = arena_take<u8>(c, N + 16);
 	JP_TRY(fwd_alloc(c, n, b));
 	JP_CUDA(cudaMemcpyAsync(d_T, h_in, N, cudaMemcpyHostToDevice, s));

@@ -27,6 +27,7 @@ struct Ctx {
 	size_t       d_io_cap = 0;
 	cudaEvent_t  ev[12] = {};
 	int          launches = 0;
+	u32          cur_n = 0;           // block length of the call in flight
 	int          sm_count = 0;
 	bool         busy = false;
 };
