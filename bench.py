@@ -202,6 +202,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     build.build()
     jp.set_devices([local])
@@ -292,8 +294,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # random 4-byte gathers over a table the size of this block's LF table (4*nlen bytes, rounded down to 2^k)
-        rand_rate = jp.debug_gather_rate(4 * nlen, 148 * 2048, 256, True)
+        # random 4-byte gathers over a table the size of this block's LF table (4*nlen bytes, rounded up to 2^k)
+        rand_rate = jp.debug_gather_rate(1 << (4 * nlen - 1).bit_length(), 148 * 2048, 256, True)
         walk_ms = (inv_acc[2] + inv_acc[3] + inv_acc[4]) / K                        # both walk kernels + ranking
         algo_bytes = 64.0 * nlen                                                    # 2 random sectors / byte
         achieved = algo_bytes / (walk_ms * 1e-3) / 1e9

@@ -275,8 +275,11 @@ constexpr u32 SG_PAIR_MAX = 256;                    // longest group the all-pai
 struct SegTile { u32 start, len; };
 
 // Slot range [start, start+len) of the groups whose head lies in window `win` (len == 0: nothing to do).
+// When `win_first` is given, the block also records its first head slot and the head of the group it had to
+// leave to the large-group route (0xffffffff = none); k_large_collect turns those into the list of large groups.
 __device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K, u32 A, int rank_bits,
-                                             u32* __restrict__ sh /*[3]*/, u32* __restrict__ has_large)
+                                             u32* __restrict__ sh /*[3]*/, u32* __restrict__ has_large,
+                                             u32* __restrict__ win_first = nullptr, u32* __restrict__ win_large = nullptr)
 {
 	const int t = threadIdx.x;
 	const u32 w0 = win * SG_WIN;
@@ -294,6 +297,7 @@ __device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K,
 	}
 	__syncthreads();
 	const u32 start = sh[0];
+	if (t == 0 && win_first) { win_first[win] = start; win_large[win] = 0xffffffffu; }
 	if (start == 0xffffffffu) return r;               // the window lies inside a group owned by an earlier block
 	u32 end;
 	if (L == A) end = A;
@@ -309,7 +313,10 @@ __device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K,
 		end = sh[2];
 		if (end == 0xffffffffu) {
 			if (lim == A) end = A;
-			else { end = sh[1]; if (t == 0 && has_large) *has_large = 1u; }   // last group spans > a window: not ours
+			else {                                        // last group spans > a window: not ours
+				end = sh[1];
+				if (t == 0 && has_large) { *has_large = 1u; if (win_large) win_large[win] = end; }
+			}
 		}
 	}
 	if (end <= start) return r;
@@ -332,7 +339,8 @@ constexpr size_t SG_SMEM_LIGHT = (size_t)SG_CAP * (4 + 4 + 1);
 __global__ void __launch_bounds__(SG_THREADS, 4) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
                                                          const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
                                                          u8* __restrict__ F, u32* __restrict__ counters /*[2]=has_large [3]=queued*/,
-                                                         u32* __restrict__ queue, int* __restrict__ err)
+                                                         u32* __restrict__ queue, u32* __restrict__ win_first, u32* __restrict__ win_large,
+                                                         int* __restrict__ err)
 {
 	extern __shared__ __align__(16) u8 sg_smem[];
 	u32* skey = reinterpret_cast<u32*>(sg_smem);        // key2 = ISA[s + h]; later the refined suffix ids
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(SG_THREADS, 4) k_seg_sort(const u64* __restric
 	__shared__ u32 sh[3];
 	__shared__ u32 wf[SG_ITEMS][SG_THREADS / 32], wb[SG_ITEMS][SG_THREADS / 32];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	const SegTile tile = seg_range(blockIdx.x, K, A, rank_bits, sh, counters + 2);
+	const SegTile tile = seg_range(blockIdx.x, K, A, rank_bits, sh, counters + 2, win_first, win_large);
 	const u32 len = tile.len, start = tile.start;
 	if (len == 0) return;
 
@@ -522,7 +530,83 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __rest
 	}
 }
 
-// ---- 5b. doubling, large groups: fetch the rank of the continuation (then global radix sort) ---------------------------------------------------
+// ---- 5b. doubling round, large groups -------------------------------------------------------------------
+// A group longer than a window (common prefixes of real text, periodic data) cannot be sorted inside one block.
+// The windows report where such groups start; k_large_collect finds where they end (the next group head of any
+// later window) and lays them out back to back; their suffixes are extracted with key (large-group id, ISA[s+h]),
+// sorted by the global radix sort, and written back in place with their head flags. Everything else in the
+// active set stays on the shared-memory route.
+__global__ void __launch_bounds__(1024) k_large_collect(u32* __restrict__ win_first, const u32* __restrict__ win_large, u32 nwin, u32 A,
+                                                        u32* __restrict__ lg_head, u32* __restrict__ lg_off, u32* __restrict__ counters /*[4] groups [5] elements*/)
+{
+	__shared__ u32 ws[32];
+	__shared__ u32 cmin[1024];
+	const u32 t = threadIdx.x;
+	const u32 per = (nwin + 1023) / 1024;
+	const u32 lo = min(nwin, t * per), hi = min(nwin, lo + per);
+	// next group head after each window: exclusive suffix minimum of win_first (in place)
+	u32 m = 0xffffffffu;
+	for (u32 c = lo; c < hi; c++) m = min(m, win_first[c]);
+	cmin[t] = m;
+	__syncthreads();
+	u32 run = 0xffffffffu;
+	for (u32 k = t + 1; k < 1024; k++) run = min(run, cmin[k]);      // 1024 x 1024 shared reads: negligible next to the sort
+	u32 cnt = 0, sum = 0;
+	for (u32 c = hi; c-- > lo;) {
+		const u32 f = win_first[c];
+		const u32 nf = min(run, A);
+		win_first[c] = nf;
+		run = min(run, f);
+		const u32 h = win_large[c];
+		if (h != 0xffffffffu) { cnt++; sum += nf - h; }
+	}
+	u32 tot_c, tot_s;
+	const u32 ic = block_incl_sum(cnt, ws, &tot_c);
+	const u32 is = block_incl_sum(sum, ws, &tot_s);
+	u32 g = ic - cnt, off = is - sum;
+	for (u32 c = lo; c < hi; c++) {
+		const u32 h = win_large[c];
+		if (h != 0xffffffffu) { lg_head[g] = h; lg_off[g] = off; off += win_first[c] - h; g++; }
+	}
+	if (t == 1023) { lg_off[tot_c] = tot_s; counters[4] = tot_c; counters[5] = tot_s; }
+}
+
+__device__ __forceinline__ u32 large_group_of(const u32* __restrict__ lg_off, u32 ng, u32 x)
+{
+	u32 lo = 0, hi = ng;                                  // last g with lg_off[g] <= x
+	while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (lg_off[mid] <= x) lo = mid; else hi = mid; }
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) k_large_extract(const u32* __restrict__ V, const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+                                                       const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 ng, u32 total,
+                                                       u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err)
+{
+	const u32 x = blockIdx.x * 256 + threadIdx.x;
+	if (x >= total) return;
+	const u32 g = large_group_of(lg_off, ng, x);
+	const u32 v = V[lg_head[g] + (x - lg_off[g])];
+	u32 p = v + h;
+	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+	LK[x] = ((u64)g << rank_bits) | (u64)__ldg(&ISA[p]);
+	LV[x] = v;
+}
+
+__global__ void __launch_bounds__(256) k_large_writeback(const u64* __restrict__ LK, const u32* __restrict__ LV, int rank_bits,
+                                                         const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 total,
+                                                         u32* __restrict__ V, u8* __restrict__ F)
+{
+	const u32 x = blockIdx.x * 256 + threadIdx.x;
+	if (x >= total) return;
+	const u64 k = LK[x];
+	const u32 g = (u32)(k >> rank_bits);
+	const u32 o = lg_off[g];
+	const u32 slot = lg_head[g] + (x - o);
+	V[slot] = LV[x];
+	F[slot] = (x == o || LK[x - 1] != k) ? 1 : 0;
+}
+
+// ---- 5c. doubling round, composite-key route for the whole active set (A/B reference: JP_BWT_FWD_GLOBAL=1) ---------------------------------------------------
 __global__ void __launch_bounds__(256) k_fwd_gather(u64* __restrict__ K, const u32* __restrict__ V, u32 A,
                                                     const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err)
 {
@@ -578,6 +662,7 @@ struct FwdBuffers {
 	int isa_region_log2;
 	u8* F;
 	u32* queue;
+	u32* win_first; u32* win_large; u32* lg_head; u32* lg_off;
 	GAgg* agg;
 	FwdMeta* meta;
 	u32* counters;
@@ -590,7 +675,7 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
 	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + 2 * Arena::align(N * 4) +
 	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align(gtiles * sizeof(GAgg)) +
-	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + Arena::align((N / SG_WIN + 16) * 4);
+	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + 5 * Arena::align((N / SG_WIN + 16) * 4);
 	JP_TRY(arena_reserve(c, total));
 	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
 	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
@@ -602,6 +687,8 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	b.rb.totals = arena_take<u32>(c, 256);
 	b.F = arena_take<u8>(c, N + 16);
 	b.queue = arena_take<u32>(c, N / SG_WIN + 16);
+	b.win_first = arena_take<u32>(c, N / SG_WIN + 16); b.win_large = arena_take<u32>(c, N / SG_WIN + 16);
+	b.lg_head = arena_take<u32>(c, N / SG_WIN + 16); b.lg_off = arena_take<u32>(c, N / SG_WIN + 16);
 	b.agg = arena_take<GAgg>(c, gtiles);
 	b.meta = arena_take<FwdMeta>(c, 1);
 	b.counters = arena_take<u32>(c, 16);
@@ -671,35 +758,59 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	u64 sectors = 2ull * (u64)n;
 	i64 h = depth;
 	int rounds = 0;
+	double large_frac_prev = 0.0;
 	while (A > 0) {
 		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
 		st->active_fraction[rounds] = (float)((double)A / (double)n);
 		sectors += 2ull * A;
-		// small groups: one fused gather + shared-memory segmented sort; it reports whether any group was too large
-		bool large = force_global;
-		if (!large) {
-			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 2 * sizeof(u32), s));
-			k_seg_sort<<<(A + SG_WIN - 1) / SG_WIN, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
-			                                                                 rank_bits, b.F, b.counters, b.queue, b.err); JP_LAUNCH(c);
+		double large_frac_now = 0.0;
+		// a round that had most of the block in over-long groups (periodic data, one-symbol runs) is followed by more
+		// of the same: skip the shared-memory kernels and sort the whole active set by composite key
+		if (!force_global && large_frac_prev <= 0.5) {
+			// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
+			// shared-memory radix kernel; groups longer than a window are reported for the large-group route
+			const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
+			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
+			k_seg_sort<<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
+			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err); JP_LAUNCH(c);
 			JP_KCHECK();
 			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 			JP_CUDA(cudaStreamSynchronize(s));
-			large = c.h_small[10] != 0;
+			const bool large = c.h_small[10] != 0;
 			const u32 queued = (u32)c.h_small[11];
-			if (!large && queued) {
+			if (queued) {
 				k_seg_sort_radix<<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
 				                                                    rank_bits, b.F, b.queue, b.err); JP_LAUNCH(c);
 				JP_KCHECK();
 				st->ms_phase[6] += (float)queued;       // tiles that needed the shared-memory radix route
 			}
-		}
-		if (!large) {
+			if (large) {
+				k_large_collect<<<1, 1024, 0, s>>>(b.win_first, b.win_large, nwin, A, b.lg_head, b.lg_off, b.counters); JP_LAUNCH(c);
+				JP_KCHECK();
+				JP_CUDA(cudaMemcpyAsync(c.h_small + 12, b.counters + 4, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+				JP_CUDA(cudaStreamSynchronize(s));
+				const u32 ng = (u32)c.h_small[12], total = (u32)c.h_small[13];
+				st->ms_phase[5] += (float)((double)total / (double)n);   // fraction of the block that went through the large-group route, summed over rounds
+				large_frac_now = (double)total / (double)A;
+				if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
+				// the gidx keys of the active set are dead once the shared-memory kernels are done: sort in the spare buffers
+				RadixBuffers lb = b.rb;
+				lb.k[0] = b.rb.k[act ^ 1]; lb.k[1] = b.rb.k[act];
+				lb.v[0] = b.rb.v[act ^ 1]; lb.v[1] = b.R;
+				k_large_extract<<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
+				                                                    lb.k[0], lb.v[0], b.err); JP_LAUNCH(c);
+				const int key_bits = rank_bits + bit_length((u64)(ng - 1));
+				const int lc = radix_sort_pairs(lb, 0, total, 0, key_bits, s, &c.launches);
+				if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+				k_large_writeback<<<(total + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, total, b.rb.v[act], b.F); JP_LAUNCH(c);
+				JP_KCHECK();
+			}
 			cur = act;
 			JP_TRY(group_step(c, b, cur, pc, false, true, A, rank_bits, s));
 		} else {
-			// some group spans more than a window: composite-key global radix sort of the whole active set
-			st->ms_phase[5] += 1.0f;                    // counts the rounds that took the global route
+			st->ms_phase[5] += (float)((double)A / (double)n);
+			large_frac_now = G * (u64)SG_WIN >= A ? 0.0 : 1.0;       // back to the segmented route once groups average under a window
 			k_fwd_gather<<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err); JP_LAUNCH(c);
 			const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
 			cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
@@ -708,6 +819,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		}
 		act = cur ^ 1; pc ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
+		large_frac_prev = large_frac_now;
 		h *= 2; rounds++;
 	}
 	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);

@@ -2,6 +2,8 @@
 // sharding over devices, host<->device staging, error and stats plumbing. No kernels live here.
 #include "bwt_internal.cuh"
 
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -45,6 +47,50 @@ int arena_reserve(Ctx& c, size_t total)
 	JP_CUDA(cudaMalloc(&c.arena.base, want));
 	c.arena.cap = want;
 	return JP_OK;
+}
+
+// ---- optional stage trace (JP_BWT_TRACE=1): per-direction totals printed to stderr at exit ---------------
+// The reference's own progress line reports CPU time (clock(), jampack.cpp:202-229); this gives the wall-clock
+// view of just this stage when it runs inside the reference's pipeline (BASELINE.json configs[3]).
+struct Trace {
+	std::atomic<long long> calls{0}, bytes{0}, wall_us{0}, dev_us{0};
+	std::atomic<long long> first_us{-1}, last_us{0};
+};
+static Trace g_trace[2];
+static std::atomic<int> g_trace_on{-1};
+static long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void trace_report()
+{
+	static const char* names[2] = {"forward", "inverse"};
+	for (int d = 0; d < 2; d++) {
+		const long long calls = g_trace[d].calls.load();
+		if (!calls) continue;
+		const double mb = g_trace[d].bytes.load() / 1e6, wall = g_trace[d].wall_us.load() / 1e6, dev = g_trace[d].dev_us.load() / 1e6;
+		const double span = (g_trace[d].last_us.load() - g_trace[d].first_us.load()) / 1e6;
+		fprintf(stderr, "[jp_bwt trace] %s: calls=%lld MB=%.1f sum_call_wall_s=%.4f sum_device_s=%.4f span_s=%.4f "
+		        "MBps_per_call=%.1f MBps_over_span=%.1f devices=%d\n", names[d], calls, mb, wall, dev, span,
+		        wall > 0 ? mb / wall : 0.0, span > 0 ? mb / span : 0.0, jp_bwt_device_count());
+	}
+}
+static bool trace_enabled()
+{
+	int v = g_trace_on.load();
+	if (v < 0) {
+		const char* e = getenv("JP_BWT_TRACE");
+		v = (e && *e && *e != '0') ? 1 : 0;
+		int expect = -1;
+		if (g_trace_on.compare_exchange_strong(expect, v) && v) atexit(trace_report);
+	}
+	return g_trace_on.load() == 1;
+}
+static void trace_add(int direction, long long bytes, long long t0, long long t1, float dev_ms)
+{
+	Trace& t = g_trace[direction];
+	t.calls++; t.bytes += bytes; t.wall_us += (t1 - t0); t.dev_us += (long long)(dev_ms * 1e3f);
+	long long expect = -1;
+	t.first_us.compare_exchange_strong(expect, t0);
+	long long prev = t.last_us.load();
+	while (prev < t1 && !t.last_us.compare_exchange_weak(prev, t1)) {}
 }
 
 // ---- context pool -----------------------------------------------------------------------------------
@@ -169,6 +215,8 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	if ((i64)len > (i64)JP_BWT_MAX_LEN * 105 / 100) { set_error_detail("block longer than 1.05 * MAX_BLOCKSIZE"); return JP_ERR_ARG; }
 	const i32 nlen = len - len % JP_BWT_UNITS;
 	*out_len = direction == 0 ? len + JP_BWT_TRAILER_BYTES : len;          // bwt.cpp:27 / :78
+	const bool tr = trace_enabled();
+	const long long t_begin = tr ? now_us() : 0;
 	CtxGuard g;
 	JP_TRY(acquire(-1, &g.c));
 	Ctx& c = *g.c;
@@ -192,6 +240,7 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high;
+	if (tr) trace_add(direction, len, t_begin, now_us(), t_stats.ms_total + t_stats.ms_h2d + t_stats.ms_d2h);
 	return JP_OK;
 }
 
