@@ -58,6 +58,7 @@ struct Trace {
 };
 static Trace g_trace[2];
 static std::atomic<int> g_trace_on{-1};
+static bool g_trace_calls = false;             // JP_BWT_TRACE=2: one line per call as well
 static long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static void trace_report()
 {
@@ -78,6 +79,7 @@ static bool trace_enabled()
 	if (v < 0) {
 		const char* e = getenv("JP_BWT_TRACE");
 		v = (e && *e && *e != '0') ? 1 : 0;
+		if (v && *e == '2') g_trace_calls = true;
 		int expect = -1;
 		if (g_trace_on.compare_exchange_strong(expect, v) && v) atexit(trace_report);
 	}
@@ -219,6 +221,7 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	const long long t_begin = tr ? now_us() : 0;
 	CtxGuard g;
 	JP_TRY(acquire(-1, &g.c));
+	const long long t_acquired = tr ? now_us() : 0;
 	Ctx& c = *g.c;
 	begin_call(c);
 	cudaStream_t s = c.own_stream;
@@ -240,7 +243,13 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high;
-	if (tr) trace_add(direction, len, t_begin, now_us(), t_stats.ms_total + t_stats.ms_h2d + t_stats.ms_d2h);
+	if (tr) {
+		const long long t_end = now_us();
+		trace_add(direction, len, t_begin, t_end, t_stats.ms_total + t_stats.ms_h2d + t_stats.ms_d2h);
+		if (g_trace_calls)
+			fprintf(stderr, "[jp_bwt call] dir=%d len=%d dev=%d t0_us=%lld wait_us=%lld call_us=%lld h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f\n", direction, len,
+			        c.device, t_begin, t_acquired - t_begin, t_end - t_begin, t_stats.ms_h2d, t_stats.ms_total, t_stats.ms_d2h);
+	}
 	return JP_OK;
 }
 

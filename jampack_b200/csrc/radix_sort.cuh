@@ -158,10 +158,156 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict
 	}
 }
 
+// ---- single-pass-per-digit variant ("onesweep": chained scan with decoupled look-back) --------------------
+// The three-kernel pass above reads the keys twice (histogram, scatter). Here one kernel does a whole digit:
+// blocks take tiles in ticket order, rank their keys, publish the tile's digit counts as an AGGREGATE word,
+// sum their predecessors' words backwards until they meet an inclusive PREFIX word, publish their own prefix
+// and scatter. The digit's global histogram (which does not depend on the order of the keys) comes from the
+// previous pass, which counts the next digit while it has the keys in registers; only the first pass needs a
+// counting kernel. A tile's predecessors hold earlier tickets, so they are running or done and publish before
+// they wait: the chain cannot deadlock; a spin cap turns any surprise into an error flag instead of a hang.
+constexpr u32 OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 1u << 31, OS_VALUE_MASK = (1u << 30) - 1;
+constexpr u32 OS_SPIN_CAP = 1u << 26;
+
+__device__ __forceinline__ void os_store(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 os_load(const u32* p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// global digit counts of one digit position (first pass only)
+__global__ void __launch_bounds__(RS_THREADS) k_os_count(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ ghist)
+{
+	__shared__ u32 h[RS_WARPS][256];
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
+	__syncthreads();
+	u32* hw = h[w];
+	for (u32 tile = blockIdx.x; (u64)tile * RS_TILE < n; tile += gridDim.x) {
+		const u32 base = tile * RS_TILE + w * (32 * RS_ITEMS);
+		#pragma unroll
+		for (int i = 0; i < RS_ITEMS; i++) {
+			const u32 p = base + i * 32 + lane;
+			const u32 d = p < n ? rs_digit(keys[p], shift) : 256u;
+			const u32 peers = __match_any_sync(0xffffffffu, d);
+			if (d < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+		}
+	}
+	__syncthreads();
+	u32 s = 0;
+	#pragma unroll
+	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
+	if (s) atomicAdd(&ghist[t], s);
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ kin, const u32* __restrict__ vin,
+                                                        u64* __restrict__ kout, u32* __restrict__ vout, u32 n, int shift,
+                                                        const u32* __restrict__ ghist, u32* __restrict__ ghist_next, int next_shift,
+                                                        u32* __restrict__ lookback, u32* __restrict__ ticket, int* __restrict__ err)
+{
+	extern __shared__ __align__(16) u8 rs_smem[];
+	u64* skey = reinterpret_cast<u64*>(rs_smem);
+	u32* sval = reinterpret_cast<u32*>(rs_smem + (size_t)RS_TILE * 8);
+	__shared__ u32 wcnt[RS_WARPS][256];
+	__shared__ u32 bin_start[256];
+	__shared__ u32 g_off[256];
+	__shared__ u32 nhist[256];
+	__shared__ u32 ws[32];
+	__shared__ u32 s_tile;
+
+	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+	const u32 lt = lanemask_lt();
+	if (t == 0) s_tile = atomicAdd(ticket, 1u);
+	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+	nhist[t] = 0;
+	__syncthreads();
+	const u32 tile = s_tile;
+	const u32 tile_base = tile * RS_TILE;
+	const u32 valid = min((u32)RS_TILE, n - tile_base);
+
+	u64 key[RS_ITEMS];
+	u32 val[RS_ITEMS];
+	const u32 wbase = tile_base + w * (32 * RS_ITEMS);
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 p = wbase + i * 32 + lane;
+		const bool ok = p < n;
+		key[i] = ok ? kin[p] : ~0ull;
+		val[i] = ok ? vin[p] : 0u;
+	}
+	u32 rank[RS_ITEMS];
+	u32* mycnt = wcnt[w];
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 d = rs_digit(key[i], shift);
+		const u32 peers = __match_any_sync(0xffffffffu, d);
+		const u32 below = __popc(peers & lt);
+		u32 before = 0;
+		if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
+		before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+		rank[i] = before + below;
+		__syncwarp();
+	}
+	if (ghist_next) {                                   // count the next digit while the keys are here
+		#pragma unroll
+		for (int i = 0; i < RS_ITEMS; i++) {
+			const bool ok = wbase + i * 32 + lane < n;
+			const u32 d = ok ? rs_digit(key[i], next_shift) : 256u;
+			const u32 peers = __match_any_sync(0xffffffffu, d);
+			if (ok && (peers & lt) == 0) atomicAdd(&nhist[d], (u32)__popc(peers));
+		}
+	}
+	__syncthreads();
+
+	// digit t: counts over warps (-> exclusive per warp), the tile's count, the digit's global base
+	u32 run = 0;
+	#pragma unroll
+	for (int k = 0; k < RS_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+	u32 cnt = run;
+	if (t == 255) cnt -= (u32)RS_TILE - valid;          // the padding keys all carry digit 255 and are not real
+	// publish, then look back
+	u32 excl = 0;
+	if (tile == 0) os_store(lookback + t, cnt | OS_FLAG_PREFIX);
+	else {
+		os_store(lookback + (size_t)tile * 256 + t, cnt | OS_FLAG_AGG);
+		u32 spins = 0;
+		for (u32 i = tile - 1;; ) {
+			const u32 sv = os_load(lookback + (size_t)i * 256 + t);
+			if ((sv >> 30) == 0) { if (++spins > OS_SPIN_CAP) { dev_fail(err, DE_FWD_ROUNDS); break; } continue; }
+			excl += sv & OS_VALUE_MASK;
+			if (sv & OS_FLAG_PREFIX) break;
+			i--;
+		}
+		os_store(lookback + (size_t)tile * 256 + t, ((excl + cnt) & OS_VALUE_MASK) | OS_FLAG_PREFIX);
+	}
+	u32 total;
+	const u32 dig_incl = block_incl_sum(ghist[t], ws, &total);          // global exclusive base of digit t
+	const u32 inc = block_incl_sum(run, ws, &total);
+	bin_start[t] = inc - run;
+	g_off[t] = (dig_incl - ghist[t]) + excl - (inc - run);
+	if (ghist_next && nhist[t]) atomicAdd(&ghist_next[t], nhist[t]);
+	__syncthreads();
+
+	#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		const u32 d = rs_digit(key[i], shift);
+		const u32 pos = bin_start[d] + mycnt[d] + rank[i];
+		skey[pos] = key[i];
+		sval[pos] = val[i];
+	}
+	__syncthreads();
+	for (u32 j = t; j < valid; j += RS_THREADS) {
+		const u64 k = skey[j];
+		const u32 dst = g_off[rs_digit(k, shift)] + j;
+		kout[dst] = k;
+		vout[dst] = sval[j];
+	}
+}
+
 struct RadixBuffers {
 	u64* k[2]; u32* v[2];
-	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries
+	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries; the look-back words of the one-sweep passes
 	u32* totals;      // 256
+	u32* os_state;    // 1024: digit histograms of the current / next pass [0..512), ticket [512]
+	int* err;
+	bool classic;     // three-kernel passes (A/B switch, and blocks of 2^30 keys or more)
 };
 
 inline size_t radix_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
@@ -174,6 +320,26 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 	// function attributes are per device; setting one is a host-only call
 	if (cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
 	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
+	if (!b.classic && n < (1u << 30)) {
+		if (cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
+		u32* gh[2] = {b.os_state, b.os_state + 256};
+		u32* ticket = b.os_state + 512;
+		cudaMemsetAsync(b.os_state, 0, 1024 * sizeof(u32), s);
+		k_os_count<<<min(tiles, 148u * 8u), RS_THREADS, 0, s>>>(b.k[cur], n, bit_lo, gh[0]);
+		*launches += 1;
+		int g = 0;
+		for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+			const bool more = shift + 8 < bit_hi;
+			cudaMemsetAsync(b.tile_hist, 0, (size_t)tiles * 256 * sizeof(u32), s);
+			cudaMemsetAsync(gh[g ^ 1], 0, 256 * sizeof(u32), s);
+			cudaMemsetAsync(ticket, 0, sizeof(u32), s);
+			k_os_pass<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n, shift, gh[g],
+			                                                     more ? gh[g ^ 1] : nullptr, shift + 8, b.tile_hist, ticket, b.err);
+			*launches += 1;
+			cur ^= 1; g ^= 1;
+		}
+		return cur;
+	}
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
 		k_rs_hist<<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride);
 		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);

@@ -56,16 +56,22 @@ def main():
         for b in range(blocks):
             synth.gen("markov2", 64 * MiB, 100 + b).tofile(f)
     out = {"blocks": blocks, "block_mib": 64, "flags": f"-b64 -t{threads}", "host_cores": os.cpu_count(), "devices": devices or "all"}
-    env = dict(os.environ, JP_BWT_TRACE="1")
+    env = dict(os.environ, JP_BWT_TRACE=arg("--trace", "1"))
     if devices:
         env["JP_BWT_DEVICES"] = devices
     jam_s, back_s = os.path.join(d, "shim.jam"), os.path.join(d, "shim.back")
     dt, err = run([shim, "c", src, jam_s, "-b64", f"-t{threads}"], env)
     out["shim_compress_s"] = round(dt, 2)
     out["shim_compress_trace"] = re.findall(r"\[jp_bwt trace\] (.*)", err)
+    calls = re.findall(r"\[jp_bwt call\] (.*)", err)
+    if calls:
+        out["compress_calls"] = calls
     dt, err = run([shim, "d", jam_s, back_s, f"-t{threads}"], env)
     out["shim_decompress_s"] = round(dt, 2)
     out["shim_decompress_trace"] = re.findall(r"\[jp_bwt trace\] (.*)", err)
+    calls = re.findall(r"\[jp_bwt call\] (.*)", err)
+    if calls:
+        out["decompress_calls"] = calls
     out["shim_round_trip"] = sha(back_s) == sha(src)
     out["jam_bytes"] = os.path.getsize(jam_s)
     out["shim_jam_sha256"] = sha(jam_s)
