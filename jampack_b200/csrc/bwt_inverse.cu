@@ -239,16 +239,27 @@ __global__ void k_inv_mark_anchors(const InvMeta* __restrict__ meta, u32* __rest
 struct AnchorTable {
 	i32 row[N_ANCHOR];
 	i32 id[N_ANCHOR];
+	u32 bits[32];                  // 1024-bit filter over the anchor rows: almost every marked row is NOT an anchor
 };
+__device__ __forceinline__ u32 anchor_hash(i32 row) { return mix32((u32)row) & 1023u; }
 
 __device__ __forceinline__ void load_anchor_table(AnchorTable& a, const InvMeta* meta)
 {
-	for (int i = threadIdx.x; i < N_ANCHOR; i += blockDim.x) { a.row[i] = meta->sorted_row[i]; a.id[i] = meta->sorted_id[i]; }
+	if (threadIdx.x < 32) a.bits[threadIdx.x] = 0;
+	__syncthreads();
+	for (int i = threadIdx.x; i < N_ANCHOR; i += blockDim.x) {
+		const i32 r = meta->sorted_row[i];
+		a.row[i] = r; a.id[i] = meta->sorted_id[i];
+		const u32 hsh = anchor_hash(r);
+		atomicOr(&a.bits[hsh >> 5], 1u << (hsh & 31));
+	}
 }
 
 // node id of the marked row `row` (byte index bi): an anchor if it is one, else the window's splitter
 __device__ __forceinline__ u32 node_of(const AnchorTable& a, i32 row, i32 bi, int log2m, u32 S)
 {
+	const u32 hsh = anchor_hash(row);
+	if (((a.bits[hsh >> 5] >> (hsh & 31)) & 1u) == 0) return (u32)bi >> log2m;
 	int lo = 0, hi = N_ANCHOR;          // first position with a.row[pos] >= row
 	while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.row[mid] < row) lo = mid + 1; else hi = mid; }
 	if (lo < N_ANCHOR && a.row[lo] == row) return S + (u32)a.id[lo];
@@ -399,23 +410,27 @@ __device__ __forceinline__ u32 symbol_of_row(const i32* __restrict__ C, i32 row)
 	return lo;
 }
 
-// cnt (< 16) low bytes of the little-endian 128-bit value a3:a2:a1:a0 to out[pos ..): words where aligned
-__device__ __forceinline__ void store_partial(u8* __restrict__ out, i32 pos, int cnt, u32 a0, u32 a1, u32 a2, u32 a3, u64 pol, bool hinted)
+// One aligned 16-byte window of the output, bytes [lo, hi) valid in (a0..a3), the rest zero. Whole words go
+// out as stores, a word shared with a neighbouring sub-chain as a RED.OR into the zeroed output -- the two
+// sub-chains own different bytes of it, so OR-ing is exact and needs no ordering. No loops, no byte stores.
+__device__ __forceinline__ void flush_window(u8* __restrict__ win, u32 lo, u32 hi, u32 a0, u32 a1, u32 a2, u32 a3)
 {
-	int j = 0;
-	while (j < cnt) {
-		if (((pos + j) & 3) == 0 && cnt - j >= 4) { st_out4(out + pos + j, a0, pol, hinted); a0 = a1; a1 = a2; a2 = a3; j += 4; }
-		else {
-			st_out1(out + pos + j, a0 & 255u, pol, hinted);
-			a0 = __funnelshift_r(a0, a1, 8); a1 = __funnelshift_r(a1, a2, 8); a2 = __funnelshift_r(a2, a3, 8); a3 >>= 8;
-			j++;
+	if (lo == 0 && hi == 16) { *reinterpret_cast<uint4*>(win) = make_uint4(a0, a1, a2, a3); return; }
+	const u64 h[2] = {((u64)a1 << 32) | a0, ((u64)a3 << 32) | a2};
+	#pragma unroll
+	for (u32 i = 0; i < 2; i++) {                       // 8-byte halves: at most two memory operations per window
+		const u32 b0 = 8 * i, wlo = max(lo, b0), whi = min(hi, b0 + 8);
+		if (whi > wlo) {
+			unsigned long long* p = reinterpret_cast<unsigned long long*>(win + b0);
+			if (whi - wlo == 8) *p = h[i];
+			else atomicOr(p, (unsigned long long)h[i]);  // result unused: compiles to RED.OR.64
 		}
 	}
 }
 
-// Pass 2: the same walk, now emitting. Bytes are produced right-to-left and shifted into a 128-bit
-// little-endian accumulator; every completed 16-byte window goes out as one aligned vector store, the
-// partial windows at either end of a sub-chain (shared with the neighbouring sub-chains) as word/byte stores.
+// Pass 2: the same walk, now emitting. A byte produced for text position q is OR-ed into its place in a
+// 128-bit image of the aligned 16-byte window around q; the window is flushed when the walk leaves it or the
+// sub-chain ends. The output block is zeroed beforehand (RED.OR merging of shared words).
 __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
                                                                i32 n, i32 step, int log2m, u32 S, const u64* __restrict__ rec,
                                                                u32* __restrict__ ticket, u8* __restrict__ out,
@@ -426,8 +441,8 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 	__syncthreads();
 	const i32 idx = meta->idx;
 	const u32 nodes = S + N_ANCHOR;
-	const bool lh = (flags & WF_LOAD_EVICT_FIRST) != 0, sh = (flags & WF_STORE_EVICT_LAST) != 0;
-	const u64 pol_ld = policy_evict_first(), pol_st = policy_evict_last();
+	const bool lh = (flags & WF_LOAD_EVICT_FIRST) != 0;
+	const u64 pol_ld = policy_evict_first();
 	WarpTickets wt = {0, 0};
 	u32 id = REC_INVALID, v = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 	i32 pos = 0, pos_end = 0;
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 			if (bi >= 0) {
 				const i64 pe = (i64)(nxt - S) * step + (u32)r;
 				if (nxt < S || pe > n || pe <= 0) dev_fail(err, DE_CHAIN_RANGE);
-				else { id = my; pos = pos_end = (i32)pe; v = ld_lf(lf + bi, pol_ld, lh); }
+				else { id = my; pos = pos_end = (i32)pe; a0 = a1 = a2 = a3 = 0; v = ld_lf(lf + bi, pol_ld, lh); }
 			}
 		}
 		if (__ballot_sync(0xffffffffu, !done) == 0) break;
@@ -456,13 +471,12 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 			if (pos <= 0) { dev_fail(err, DE_CHAIN_RANGE); id = REC_INVALID; }
 			else {
 				pos--;
-				a3 = __funnelshift_l(a2, a3, 8); a2 = __funnelshift_l(a1, a2, 8); a1 = __funnelshift_l(a0, a1, 8); a0 = (a0 << 8) | c;
-				if ((pos & 15) == 0) {
-					if (pos + 16 <= pos_end) st_out16(out + pos, a0, a1, a2, a3, pol_st, sh);
-					else store_partial(out, pos, pos_end - pos, a0, a1, a2, a3, pol_st, sh);
-				} else if (stop) {
-					const i32 top = min(pos_end, (pos & ~15) + 16);
-					store_partial(out, pos, top - pos, a0, a1, a2, a3, pol_st, sh);
+				const u32 k = ((u32)pos >> 2) & 3u, bits = c << (((u32)pos & 3u) * 8);
+				a0 |= (k == 0) ? bits : 0u; a1 |= (k == 1) ? bits : 0u; a2 |= (k == 2) ? bits : 0u; a3 |= (k == 3) ? bits : 0u;
+				if (((u32)pos & 15u) == 0 || stop) {
+					const i32 wbase = pos & ~15;
+					flush_window(out + wbase, (u32)(pos - wbase), (u32)min(16, pos_end - wbase), a0, a1, a2, a3);
+					a0 = a1 = a2 = a3 = 0;
 				}
 				if (stop) id = REC_INVALID;
 			}
@@ -563,6 +577,7 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[4], s));
+	JP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nlen, s));               // shared words of neighbouring sub-chains are merged by RED.OR
 	const int wb2 = walker_blocks(c, (const void*)k_inv_walk_emit);
 	k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err, walk_flags()); JP_LAUNCH(c);
 	JP_KCHECK();
