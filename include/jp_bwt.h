@@ -76,6 +76,13 @@ int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t
  * this way on its own device copy. */
 int jp_bwt_inverse_device_consume(uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream);
 
+/* ---- the suffix sorter on its own ------------------------------------------------
+ * jp_bwt_suffix_array replaces divsufsort(T, SA, n) (divsufsort.cpp:1721, contract divsufsort.hpp:37-45) for its
+ * second call site, the -m2 suffix-array match finder of lz77.cpp:141: sa[0..n) receives the suffix array of
+ * in[0..n), a proper prefix sorting before its extensions. jampack_b200/host/divsufsort_shim.cpp binds it under the
+ * reference's own symbol name. n == 0 is a no-op. Returns JP_OK or an error code. */
+int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa);
+
 /* ---- device selection (block sharding) ---------------------------------------------
  * Default: every visible device, or the list in the environment variable JP_BWT_DEVICES ("0,1,2").
  * jp_bwt_set_devices replaces the list (n = 0 restores the default). Returns JP_OK or an error. */
@@ -118,11 +125,9 @@ const char* jp_bwt_version(void);
  * jp_bwt_debug_lf: builds the inverse's LF table for in[0..nlen) on device 0 and copies it back
  *   (marker bits stripped): lf[i] = 1 + C[in[i]] + #{j < i : in[j] == in[i]}, ctable[c] = #{in[j] < c}.
  *   This is the inverse permutation of the reference's Map (bwt.cpp:171-174): Map[lf[i]-1] == i + (i >= idx).
- * jp_bwt_debug_suffix_array: the forward's suffix array of in[0..n) (divsufsort contract).
  * jp_bwt_debug_gather_rate: random 4-byte gather micro-benchmark over a table of `table_bytes`
  *   (`chains` dependent walkers, `steps` each); returns sectors/s, or a negative error code. */
 int jp_bwt_debug_lf(const uint8_t* in, int32_t nlen, int32_t* lf, int32_t* ctable /*[257]*/);
-int jp_bwt_debug_suffix_array(const uint8_t* in, int32_t n, int32_t* sa);
 double jp_bwt_debug_gather_rate(uint64_t table_bytes, int32_t chains, int32_t steps, int dependent);
 
 #ifdef __cplusplus

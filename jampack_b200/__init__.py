@@ -73,7 +73,7 @@ def lib():
         L.jp_bwt_last_error_detail.restype = C.c_char_p
         L.jp_bwt_version.restype = C.c_char_p
         L.jp_bwt_debug_lf.argtypes = [C.c_void_p, C.c_int32, _i32p, _i32p]
-        L.jp_bwt_debug_suffix_array.argtypes = [C.c_void_p, C.c_int32, _i32p]
+        L.jp_bwt_suffix_array.argtypes = [C.c_void_p, C.c_int32, _i32p]
         L.jp_bwt_debug_gather_rate.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int]
         L.jp_bwt_debug_gather_rate.restype = C.c_double
         _lib = L
@@ -83,7 +83,7 @@ def lib():
 EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device", "jp_bwt_inverse_device_consume",
            "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free",
            "jp_bwt_last_stats", "jp_bwt_strerror", "jp_bwt_last_error_detail", "jp_bwt_version",
-           "jp_bwt_debug_lf", "jp_bwt_debug_suffix_array", "jp_bwt_debug_gather_rate"]
+           "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate"]
 
 
 def _check(rc, what):
@@ -241,11 +241,15 @@ def debug_lf(bwt_bytes):
     return lf, ct
 
 
-def debug_suffix_array(text):
+def suffix_array(text):
+    """The forward transform's suffix sorter on its own: divsufsort(T, SA, n) semantics (reference divsufsort.hpp:37-45)."""
     t = np.ascontiguousarray(text, dtype=np.uint8)
     sa = np.empty(t.size, dtype=np.int32)
-    _check(lib().jp_bwt_debug_suffix_array(t.ctypes.data, t.size, sa.ctypes.data_as(_i32p)), "jp_bwt_debug_suffix_array")
+    _check(lib().jp_bwt_suffix_array(t.ctypes.data, t.size, sa.ctypes.data_as(_i32p)), "jp_bwt_suffix_array")
     return sa
+
+
+debug_suffix_array = suffix_array
 
 
 def debug_gather_rate(table_bytes, chains, steps, dependent=True):

@@ -336,11 +336,16 @@ int jp_bwt_debug_lf(const uint8_t* in, int32_t nlen, int32_t* lf, int32_t* ctabl
 	CtxGuard g; JP_TRY(acquire(-1, &g.c)); begin_call(*g.c);
 	return debug_lf(*g.c, in, nlen, lf, ctable);
 }
-int jp_bwt_debug_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
+int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
 {
-	if (!in || !sa || n < 0) return JP_ERR_ARG;
+	if (n < 0 || (n > 0 && (!in || !sa))) { set_error_detail("null pointer or negative length"); return JP_ERR_ARG; }
+	if ((i64)n > (i64)JP_BWT_MAX_LEN * 105 / 100) { set_error_detail("block longer than 1.05 * MAX_BLOCKSIZE"); return JP_ERR_ARG; }
 	CtxGuard g; JP_TRY(acquire(-1, &g.c)); begin_call(*g.c);
-	return debug_suffix_array(*g.c, in, n, sa);
+	if (n == 0) return JP_OK;
+	const int rc = debug_suffix_array(*g.c, in, n, sa);
+	t_stats.kernel_launches = g.c->launches;
+	t_stats.device_bytes = g.c->arena.high;
+	return rc;
 }
 double jp_bwt_debug_gather_rate(uint64_t table_bytes, int32_t chains, int32_t steps, int dependent)
 {

@@ -76,6 +76,8 @@ def ref():
         L.ref_bwt_inverse_batch.argtypes = [pp, _i32p, pp, C.c_int, C.c_int, C.c_int]
         L.ref_bwt_inverse_batch.restype = C.c_double
         L.ref_core_count.restype = C.c_int
+        L.ref_divsufsort.argtypes = [_u8p, _i32p, C.c_int]
+        L.ref_divsufsort.restype = C.c_int
         _ref = L
     return _ref
 
@@ -137,9 +139,13 @@ def build_map(B, nlen, idx):
     return M, Ct
 
 
-def suffix_array(T):
+def suffix_array(T, impl="port"):
+    """impl="ref": the reference's divsufsort() itself (divsufsort.cpp:1721)."""
     T = np.ascontiguousarray(T, dtype=np.uint8)
     SA = np.empty(T.size, dtype=np.int32)
-    rc = port().jpo_suffix_array_export(_ptr(T), _ptr(SA, _i32p), T.size)
+    if impl == "ref":
+        rc = ref().ref_divsufsort(_ptr(T), _ptr(SA, _i32p), T.size)
+    else:
+        rc = port().jpo_suffix_array_export(_ptr(T), _ptr(SA, _i32p), T.size)
     assert rc == 0
     return SA

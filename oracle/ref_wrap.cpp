@@ -61,6 +61,9 @@ double ref_bwt_inverse_batch(const unsigned char* const* ins, const int* lens_wi
 	return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+/* divsufsort.cpp:1721 itself (second call site: lz77.cpp:141) */
+int ref_divsufsort(const unsigned char* T, int* SA, int n) { return divsufsort(T, SA, n); }
+
 int ref_core_count(void) { return (int)GetCoreCount(); }
 
 }

@@ -271,3 +271,55 @@ def test_reference_pipeline_with_shim_is_byte_identical(jp, orc, golden, tmp_pat
     back_t = tmp_path / "back_t.bin"
     subprocess.run([shim, "d", str(jam_s), str(back_t), "-T"], check=True, stdout=subprocess.DEVNULL, timeout=600)
     assert back_t.read_bytes() == T.tobytes()
+
+
+# ---- widening: the suffix sorter under the reference's second divsufsort call site ------
+@pytest.mark.parametrize("kind,n,seed", [("kat_extremes", 1, 0), ("kat_extremes", 2, 0), ("uniform", 3, 1), ("alla", 1000, 0),
+                                         ("markov2", 100003, 2), ("repetitive", 300001, 3), ("uniform", MiB + 1, 4),
+                                         ("markov2", 2 * MiB, 6)])
+def test_suffix_array_equals_divsufsort(jp, orc, kind, n, seed):
+    """jp_bwt_suffix_array == divsufsort(T, SA, n) (divsufsort.cpp:1721) for any length, not only multiples of 120."""
+    T = orc.gen(kind, n, seed)
+    want = orc.suffix_array(T, "ref") if orc.ref() is not None else orc.suffix_array(T)
+    got = jp.suffix_array(T)
+    assert (got == want).all()
+    assert jp.last_stats().kernel_launches > 0
+    assert jp.suffix_array(np.zeros(0, dtype=np.uint8)).size == 0
+
+
+def test_text_with_long_repeats_takes_the_large_group_route(jp, orc):
+    """Natural-language-like input: short groups, groups that need the shared-memory radix kernel, and groups longer
+    than a window (repeated paragraphs) in the same block -- all three refinement routes must agree with the oracle."""
+    rng = np.random.default_rng(7)
+    words = [bytes(rng.integers(97, 123, rng.integers(2, 9)).astype(np.uint8)) for _ in range(300)]
+    para = b" ".join(words[i] for i in rng.integers(0, 300, 4000))
+    parts = []
+    for r in range(60):
+        parts.append(para[: rng.integers(2000, len(para))])
+        parts.append(b" ".join(words[i] for i in rng.integers(0, 300, 3000)))
+        parts.append(b"=" * int(rng.integers(10, 9000)))
+    T = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    T = T[: T.size - T.size % 120 + 7]
+    want = orc.forward(T, _impl(orc))
+    got = jp.forward(T)
+    st = jp.last_stats()
+    assert (got == want).all()
+    assert st.ms_phase[5] > 0, "expected some suffixes on the large-group route"
+    assert (jp.inverse(got) == T).all()
+
+
+def test_reference_pipeline_m2_uses_gpu_suffix_sorter(jp, orc, tmp_path):
+    """-m2 (lz77.cpp:134-146) with divsufsort() bound to jp_bwt_suffix_array: same .jam bytes as the reference."""
+    shim = os.path.join(ROOT, "oracle", "_ref", "Jampack_shim_m2")
+    ref = os.path.join(ROOT, "oracle", "_ref", "Jampack_ref")
+    if not (os.path.isfile(shim) and os.path.isfile(ref)):
+        pytest.skip("oracle/_ref binaries did not travel")
+    T = orc.gen("markov2", MiB // 2, 77)          # the match finder itself is "incredibly slow" (lz77.cpp:134): keep it small
+    src = tmp_path / "in.bin"
+    T.tofile(src)
+    jam_s, jam_r, back = tmp_path / "s.jam", tmp_path / "r.jam", tmp_path / "back.bin"
+    subprocess.run([shim, "c", str(src), str(jam_s), "-m2", "-b1", "-t2"], check=True, stdout=subprocess.DEVNULL, timeout=900)
+    subprocess.run([ref, "c", str(src), str(jam_r), "-m2", "-b1", "-t2"], check=True, stdout=subprocess.DEVNULL, timeout=900)
+    assert jam_s.read_bytes() == jam_r.read_bytes()
+    subprocess.run([shim, "d", str(jam_r), str(back), "-t2"], check=True, stdout=subprocess.DEVNULL, timeout=900)
+    assert back.read_bytes() == T.tobytes()
