@@ -179,7 +179,7 @@ def workload_config(args, n):
                         "(BASELINE.json configs[1]); 4 blocks in flight per GPU per step, as the reference's block loop keeps several "
                         "blocks in flight (jampack.cpp:215-219, :313-317); single-block latency under single_stream",
             "block_bytes": n, "units": 120,
-            "l2": "per-step working set 6N = %d MB exceeds the 126 MB L2; no explicit flush" % (6 * n // 10**6)}
+            "l2": "per-block working set 6N = %d MB %s the 126 MB L2; no explicit flush" % (6 * n // 10**6, "exceeds" if 6 * n > 126e6 else "fits in")}
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------

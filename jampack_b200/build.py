@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpbwt.so")
 SOURCES = ["jp_bwt_api.cu", "bwt_inverse.cu", "bwt_forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--use_fast_math"]
+              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--use_fast_math", "-DRS_SCATTER_MIN_BLOCKS=3"]
 
 
 def _stale():

@@ -148,33 +148,51 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict
 	}
 }
 
-// single block: exclusive scan of the tile aggregates in place; totals -> out[0] = survivors, out[1] = groups
+// single block: exclusive scan of the tile aggregates in place; totals -> out[0] = survivors, out[1] = groups.
+// Each warp owns a contiguous range and walks it 32 aggregates at a time (coalesced 512 B rows, one warp scan per
+// row); the 32 warp totals are stitched through shared memory.
+__device__ __forceinline__ GAgg gagg_combine(const GAgg& a, const GAgg& b) { GAgg r; r.mh = max(a.mh, b.mh); r.ns = a.ns + b.ns; r.ng = a.ng + b.ng; r.pad = 0; return r; }
+__device__ __forceinline__ GAgg gagg_shfl_up(const GAgg& a, int o)
+{
+	GAgg r; r.mh = __shfl_up_sync(0xffffffffu, a.mh, o); r.ns = __shfl_up_sync(0xffffffffu, a.ns, o); r.ng = __shfl_up_sync(0xffffffffu, a.ng, o); r.pad = 0; return r;
+}
+__device__ __forceinline__ GAgg gagg_warp_incl(GAgg v)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const GAgg t = gagg_shfl_up(v, o); if ((int)lane_id() >= o) v = gagg_combine(t, v); }
+	return v;
+}
 __global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg, int tiles, u32* __restrict__ out)
 {
-	__shared__ i32 wmh[32];
-	__shared__ u32 wns[32], wng[32];
+	__shared__ GAgg wtot[32];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	const int per = (tiles + 1023) / 1024;
-	const int lo = min(tiles, t * per), hi = min(tiles, lo + per);
-	i32 mh = -1; u32 ns = 0, ng = 0;
-	for (int k = lo; k < hi; k++) { const GAgg a = agg[k]; mh = max(mh, a.mh); ns += a.ns; ng += a.ng; }
-	// inclusive scan across threads
-	const i32 imh = warp_incl_max(mh); const u32 ins = warp_incl_sum(ns), ing = warp_incl_sum(ng);
-	if (lane == 31) { wmh[w] = imh; wns[w] = ins; wng[w] = ing; }
+	const int rows = (tiles + 31) / 32;                  // rows of 32 aggregates
+	const int rows_per_warp = (rows + 31) / 32;
+	const int r0 = min(rows, w * rows_per_warp), r1 = min(rows, r0 + rows_per_warp);
+	GAgg ident; ident.mh = -1; ident.ns = 0; ident.ng = 0; ident.pad = 0;
+	GAgg acc = ident;
+	for (int r = r0; r < r1; r++) { const int k = r * 32 + lane; if (k < tiles) acc = gagg_combine(acc, agg[k]); }
+	acc = gagg_warp_incl(acc);
+	if (lane == 31) wtot[w] = acc;
 	__syncthreads();
-	i32 pmh = -1; u32 pns = 0, png = 0;           // aggregate of all earlier warps
-	for (int k = 0; k < w; k++) { pmh = max(pmh, wmh[k]); pns += wns[k]; png += wng[k]; }
-	// exclusive prefix for this thread
-	i32 emh = __shfl_up_sync(0xffffffffu, imh, 1); u32 ens = __shfl_up_sync(0xffffffffu, ins, 1), eng = __shfl_up_sync(0xffffffffu, ing, 1);
-	if (lane == 0) { emh = -1; ens = 0; eng = 0; }
-	emh = max(emh, pmh); ens += pns; eng += png;
-	for (int k = lo; k < hi; k++) {
-		const GAgg a = agg[k];
-		GAgg e; e.mh = emh; e.ns = ens; e.ng = eng; e.pad = 0;
-		agg[k] = e;
-		emh = max(emh, a.mh); ens += a.ns; eng += a.ng;
+	GAgg carry = ident;
+	for (int k = 0; k < w; k++) carry = gagg_combine(carry, wtot[k]);
+	for (int r = r0; r < r1; r++) {
+		const int k = r * 32 + lane;
+		const GAgg v = k < tiles ? agg[k] : ident;
+		const GAgg inc = gagg_warp_incl(v);
+		GAgg ex = gagg_shfl_up(inc, 1);
+		if (lane == 0) ex = ident;
+		ex = gagg_combine(carry, ex);
+		if (k < tiles) agg[k] = ex;
+		GAgg rowtot; rowtot.mh = __shfl_sync(0xffffffffu, inc.mh, 31); rowtot.ns = __shfl_sync(0xffffffffu, inc.ns, 31); rowtot.ng = __shfl_sync(0xffffffffu, inc.ng, 31); rowtot.pad = 0;
+		carry = gagg_combine(carry, rowtot);
 	}
-	if (t == 1023) { out[0] = pns + ins; out[1] = png + ing; }
+	if (t == 1023) {
+		GAgg all = ident;
+		for (int k = 0; k < 32; k++) all = gagg_combine(all, wtot[k]);
+		out[0] = all.ns; out[1] = all.ng;
+	}
 }
 
 // All GS_SUB sub-tiles of a tile are loaded up front (GS_SUB independent loads per array in flight), scanned

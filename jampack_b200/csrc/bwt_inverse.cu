@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_lf(const u8* __restrict__ b
 			const u32 src = __shfl_sync(0xffffffffu, word[r], 8 * k + (lane >> 2));
 			const i64 gp = seg + r * 128 + k * 32 + lane;
 			const bool valid = gp < n;
-			const u32 c = valid ? ((src >> (8 * (lane & 3))) & 255u) : 256u;
-			const u32 peers = __match_any_sync(0xffffffffu, c);
+			const u32 c = valid ? ((src >> (8 * (lane & 3))) & 255u) : 0u;
+			const u32 vmask = __ballot_sync(0xffffffffu, valid);
+			const u32 same = match_any8_adaptive<28>(c);                // every lane takes part
+			const u32 peers = valid ? (same & vmask) : ~vmask;       // bytes past the end only match each other
 			const u32 below = __popc(peers & lt);
 			u32 before = 0;
 			if (below == 0 && valid) { before = mycnt[c]; mycnt[c] = before + __popc(peers); }

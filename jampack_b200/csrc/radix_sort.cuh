@@ -36,9 +36,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ 
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 p = base + i * 32 + lane;
 		// keys of neighbouring suffixes often share a digit: aggregate inside the warp before the atomic
-		const u32 d = p < n ? rs_digit(keys[p], shift) : 256u;
-		const u32 peers = __match_any_sync(0xffffffffu, d);
-		if (d < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+		const bool ok = p < n;
+		const u32 d = ok ? rs_digit(keys[p], shift) : 0u;
+		const u32 peers = match_any8_adaptive(d) & __ballot_sync(0xffffffffu, ok);
+		if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
 	}
 	__syncthreads();
 	u32 s = 0;
@@ -86,7 +87,10 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 	}
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin,
+#ifndef RS_SCATTER_MIN_BLOCKS
+#define RS_SCATTER_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin,
                                                            u64* __restrict__ kout, u32* __restrict__ vout,
                                                            const u32* __restrict__ tile_off, u32 stride, u32 n, int shift)
 {
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64* __restrict
 	#pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 d = rs_digit(key[i], shift);
-		const u32 peers = __match_any_sync(0xffffffffu, d);
+		const u32 peers = match_any8_adaptive(d);
 		const u32 below = __popc(peers & lt);
 		u32 before = 0;
 		if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ 
 	#pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 d = rs_digit(key[i], shift);
-		const u32 peers = __match_any_sync(0xffffffffu, d);
+		const u32 peers = match_any8_adaptive(d);
 		const u32 below = __popc(peers & lt);
 		u32 before = 0;
 		if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
