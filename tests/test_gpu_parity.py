@@ -323,3 +323,26 @@ def test_reference_pipeline_m2_uses_gpu_suffix_sorter(jp, orc, tmp_path):
     assert jam_s.read_bytes() == jam_r.read_bytes()
     subprocess.run([shim, "d", str(jam_r), str(back), "-t2"], check=True, stdout=subprocess.DEVNULL, timeout=900)
     assert back.read_bytes() == T.tobytes()
+
+
+def test_consume_variant_and_trace(jp, orc, tmp_path):
+    """jp_bwt_inverse_device_consume gives the same block while keeping the workspace at the LF table + histograms
+    (the records live in the dead input block); JP_BWT_TRACE prints the stage's wall-clock totals at exit."""
+    import torch
+    n = 8 * MiB
+    T = orc.gen("markov2", n, 3)
+    B = jp.forward(T)
+    d_in = torch.from_numpy(B.copy()).cuda()
+    out_a = jp.inverse_device(d_in)
+    bytes_const = jp.last_stats().device_bytes
+    out_b = jp.inverse_device(d_in.clone(), consume=True)
+    bytes_consume = jp.last_stats().device_bytes
+    assert torch.equal(out_a, out_b) and (out_a.cpu().numpy()[:n] == T).all()
+    assert bytes_consume < bytes_const and bytes_consume <= 4 * n + n // 32 + (1 << 20)
+    code = ("import numpy as np, jampack_b200 as jp; x = np.arange(120 * 5000, dtype=np.uint32).astype(np.uint8); "
+            "assert (jp.inverse(jp.forward(x)) == x).all()")
+    r = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, JP_BWT_TRACE="2"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "[jp_bwt trace] forward: calls=1" in r.stderr and "[jp_bwt trace] inverse: calls=1" in r.stderr
+    assert r.stderr.count("[jp_bwt call]") == 2
