@@ -50,7 +50,7 @@ struct InvMeta {
 __global__ void k_inv_prepare(const u8* __restrict__ in, i32 len, i32 nlen, u8* __restrict__ out,
                               InvMeta* __restrict__ meta, int* __restrict__ err)
 {
-	__shared__ i32 row[N_ANCHOR];
+	__shared__ i32 row[N_ANCHOR + 3];   // padded: the rank loop below is vectorised into 8-byte reads
 	const int t = threadIdx.x;
 	if (t < JP_BWT_UNITS) {
 		const u8* p = in + len + 4 * t;

@@ -72,10 +72,12 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 	for (u32 base = 0; base < tiles; base += 1024) {
 		const u32 k = base + t * 4;
 		uint4 v = make_uint4(0, 0, 0, 0);
-		if (k < tiles) v = *reinterpret_cast<const uint4*>(row + k);   // rows are padded to a multiple of 4 entries
-		if (k + 1 >= tiles) v.y = 0;
-		if (k + 2 >= tiles) v.z = 0;
-		if (k + 3 >= tiles) v.w = 0;
+		if (k + 3 < tiles) v = *reinterpret_cast<const uint4*>(row + k);   // rows are padded to a multiple of 4 entries
+		else {                                                           // the padding itself is never read
+			if (k < tiles) v.x = row[k];
+			if (k + 1 < tiles) v.y = row[k + 1];
+			if (k + 2 < tiles) v.z = row[k + 2];
+		}
 		const u32 sum = v.x + v.y + v.z + v.w;
 		u32 total;
 		const u32 inc = block_incl_sum(sum, ws, &total);

@@ -113,6 +113,11 @@ def main():
     medium = [("markov2", MiB, 1), ("uniform", MiB, 2), ("repetitive", MiB, 3), ("alla", MiB, 0), ("markov2", 8 * MiB, 1)]
     big = [("markov2", 64 * MiB, 1), ("uniform", 64 * MiB, 2), ("repetitive", 64 * MiB, 3), ("alla", 64 * MiB, 0)]
     res = []
+    if "--sanitize" in sys.argv:      # small cases only: meant to run under compute-sanitizer
+        medium = [("markov2", 300000, 1), ("alla", 200000, 0), ("repetitive", 400000, 3)]
+        import numpy as np
+        rng = np.random.default_rng(3)
+        words = [bytes(rng.integers(97, 123, rng.integers(2, 9)).astype(np.uint8)) for _ in range(50)]
     if ONLY in (None, "inv"):
         for c in small + medium[:3]:
             if c[1] >= 120:
