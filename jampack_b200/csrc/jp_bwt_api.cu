@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 namespace jp {
@@ -104,6 +105,8 @@ struct Pool {
 	std::vector<int> devices;
 	bool devices_ready = false;
 	std::vector<std::unique_ptr<Ctx>> ctxs;
+	std::vector<int> pending;          // contexts being created, per visible device (creation runs outside the lock)
+	std::vector<int> state;            // per visible device: 0 cold, 1 primary context coming up, 2 usable
 	unsigned rr = 0;
 };
 static Pool g_pool;
@@ -131,7 +134,13 @@ static int init_devices_locked()
 	}
 	if (g_pool.devices.empty()) for (int i = 0; i < n; i++) g_pool.devices.push_back(i);
 	g_pool.devices_ready = true;
+	g_pool.pending.assign((size_t)(n > 0 ? n : 1), 0);
+	g_pool.state.assign((size_t)(n > 0 ? n : 1), 0);
 	if (g_pool.devices.empty()) { set_error_detail("no CUDA device visible; this stage has no CPU path"); return JP_ERR_NO_DEVICE; }
+	// Only the first configured device is brought up here. A primary context costs about a second on these parts
+	// and the driver creates them one after the other (measured: first batch of a 4-GPU run waited 3-5 s), so the
+	// other devices come up in the background the first time the usable ones are saturated (warm_next_device).
+	g_pool.state[g_pool.devices[0]] = 2;
 	return JP_OK;
 }
 
@@ -140,12 +149,11 @@ static int create_ctx(int device, Ctx** out)
 	std::unique_ptr<Ctx> c(new Ctx());
 	c->device = device;
 	JP_CUDA(cudaSetDevice(device));
-	{
-		// The LF walk and the rank gathers use 4 bytes of every sector they touch: ask L2 to fetch single 32 B
-		// sectors on a miss instead of promoting to 64/128 B (ncu: 3.3 DRAM sectors per gather with the default).
-		size_t gran = 32;
-		if (const char* e = getenv("JP_BWT_L2_FETCH")) { long v = atol(e); if (v == 32 || v == 64 || v == 128) gran = (size_t)v; }
-		if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();   // a hint; never fatal
+	if (const char* e = getenv("JP_BWT_L2_FETCH")) {
+		// Experiment switch only. cudaLimitMaxL2FetchGranularity = 32/64/128 was measured to change nothing on B200:
+		// a random 4-byte gather costs ~2.7 DRAM sectors whatever the hint (profiles/README.md).
+		const long v = atol(e);
+		if ((v == 32 || v == 64 || v == 128) && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) cudaGetLastError();
 	}
 	JP_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	JP_CUDA(cudaMallocHost(&c->h_small, 64 * sizeof(int)));
@@ -153,26 +161,82 @@ static int create_ctx(int device, Ctx** out)
 	JP_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
 	c->busy = true;
 	*out = c.get();
+	std::lock_guard<std::mutex> lk(g_pool.mu);
 	g_pool.ctxs.push_back(std::move(c));
 	return JP_OK;
 }
 
-// device < 0: next device in round-robin order (whole blocks are the unit of sharding)
+// Starts bringing up one more configured device (detached; joins the pool when its primary context exists).
+static void warm_next_device_locked()
+{
+	for (int d : g_pool.devices) if (g_pool.state[d] == 1) return;          // one at a time: the driver serialises them anyway
+	for (int d : g_pool.devices) {
+		if (g_pool.state[d] != 0) continue;
+		g_pool.state[d] = 1;
+		static bool hooked = false;
+		if (!hooked) {                                           // never tear the runtime down under a device that is coming up
+			hooked = true;
+			atexit([] {
+				for (int spin = 0; spin < 10000; spin++) {
+					{ std::lock_guard<std::mutex> lk(g_pool.mu); bool busy = false; for (int st : g_pool.state) busy |= (st == 1); if (!busy) return; }
+					std::this_thread::sleep_for(std::chrono::milliseconds(1));
+				}
+			});
+		}
+		std::thread([d] {
+			const bool ok = cudaSetDevice(d) == cudaSuccess && cudaFree(0) == cudaSuccess;
+			{ std::lock_guard<std::mutex> lk(g_pool.mu); g_pool.state[d] = ok ? 2 : 3; }   // 3: unusable, never retried
+			g_pool.cv.notify_all();
+		}).detach();
+		return;
+	}
+}
+
+// device < 0: the configured device with the fewest blocks in flight (ties go round-robin) -- whole blocks are
+// the unit of sharding. A new context is created outside the pool lock, so first calls on different devices do
+// not queue behind each other.
 static int acquire(int device, Ctx** out)
 {
 	std::unique_lock<std::mutex> lk(g_pool.mu);
 	JP_TRY(init_devices_locked());
-	if (device < 0) device = g_pool.devices[g_pool.rr++ % g_pool.devices.size()];
-	else if (device >= visible_devices()) { set_error_detail("device %d not visible", device); return JP_ERR_NO_DEVICE; }
+	const bool any = device < 0;
+	bool waited = false;
+	if (!any && device >= (int)g_pool.pending.size()) { set_error_detail("device %d not visible", device); return JP_ERR_NO_DEVICE; }
 	for (;;) {
-		int have = 0;
+		if (any) {
+			int best = -1, best_load = 1 << 30;
+			const size_t nd = g_pool.devices.size();
+			for (size_t k = 0; k < nd; k++) {
+				const int d = g_pool.devices[(g_pool.rr + k) % nd];
+				if (g_pool.state[d] != 2) continue;
+				int load = g_pool.pending[d];
+				for (auto& c : g_pool.ctxs) if (c->device == d && c->busy) load++;
+				if (load < best_load) { best_load = load; best = d; }
+			}
+			device = best;
+			if (best_load < MAX_CTX_PER_DEVICE) g_pool.rr++;
+			else if (waited) warm_next_device_locked();          // every usable device has stayed full: widen the pool meanwhile
+		} else if (g_pool.state[device] != 2) {                  // an explicitly named device is brought up on the spot
+			g_pool.state[device] = 2;
+		}
+		int have = g_pool.pending[device];
 		for (auto& c : g_pool.ctxs) {
 			if (c->device != device) continue;
 			have++;
 			if (!c->busy) { c->busy = true; *out = c.get(); lk.unlock(); JP_CUDA(cudaSetDevice(device)); return JP_OK; }
 		}
-		if (have < MAX_CTX_PER_DEVICE) return create_ctx(device, out);
-		g_pool.cv.wait(lk);
+		if (have < MAX_CTX_PER_DEVICE) {
+			g_pool.pending[device]++;
+			lk.unlock();
+			const int rc = create_ctx(device, out);
+			lk.lock();
+			g_pool.pending[device]--;
+			lk.unlock();
+			if (rc != JP_OK) g_pool.cv.notify_all();
+			return rc;
+		}
+		// short blocks clear a full pool in milliseconds; only a pool that stays full is worth another device's start-up
+		waited = g_pool.cv.wait_for(lk, std::chrono::milliseconds(50)) == std::cv_status::timeout || waited;
 	}
 }
 
@@ -292,6 +356,9 @@ int jp_bwt_set_devices(const int* ids, int n)
 	for (int i = 0; i < n; i++) { if (ids[i] < 0 || ids[i] >= vis) { set_error_detail("device %d not visible", ids[i]); return JP_ERR_ARG; } d.push_back(ids[i]); }
 	g_pool.devices = d;
 	g_pool.devices_ready = true;
+	if (g_pool.pending.size() < (size_t)vis) g_pool.pending.resize((size_t)vis, 0);
+	if (g_pool.state.size() < (size_t)vis) g_pool.state.resize((size_t)vis, 0);
+	if (g_pool.state[d[0]] == 0) g_pool.state[d[0]] = 2;
 	g_pool.rr = 0;
 	return JP_OK;
 }
