@@ -23,7 +23,7 @@ namespace jp {
 
 struct FwdMeta {
 	u32 code[256];
-	i32 sigma, bits, depth;
+	i32 sigma, bits, depth, key_bits;   // bits: per symbol (reported); depth: symbols per key; key_bits: bit length of the largest key
 	u32 hist[256];
 };
 
@@ -59,10 +59,17 @@ __global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
 	const u32 inc = block_incl_sum(present, ws, &total);
 	meta->code[t] = present ? inc : 0u;            // codes 1..sigma in byte order
 	if (t == 0) {
-		const int bits = bit_length((u64)total);   // codes 0..sigma need bit_length(sigma) bits
+		// Keys are mixed-radix numbers in base sigma+1 (digit 0 = end of string): as many symbols as fit below 2^63.
+		// Bit fields would waste the gap between sigma+1 and the next power of two -- 65 code values in 7-bit fields
+		// give 9 symbols per key, base 65 gives 10 (and 27 instead of 21 for a 4-symbol block). Lexicographic order of
+		// the symbol strings is the numeric order of the keys either way.
+		const u64 base = (u64)total + 1;
+		int depth = 0; u64 span = 1;                // span = base^depth
+		while (depth < 63 && span <= (((u64)1 << 63) - 1) / base) { span *= base; depth++; }
 		meta->sigma = (i32)total;
-		meta->bits = bits;
-		meta->depth = 64 / bits;
+		meta->bits = bit_length((u64)total);
+		meta->depth = depth;
+		meta->key_bits = bit_length(span - 1);
 	}
 }
 
@@ -75,7 +82,8 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 	__shared__ u16 code[256];
 	const int t = threadIdx.x;
 	code[t] = (u16)meta->code[t];
-	const int bits = meta->bits, depth = meta->depth;
+	const int depth = meta->depth;
+	const u64 radix = (u64)meta->sigma + 1;
 	__syncthreads();
 	const i64 base = (i64)blockIdx.x * KEY_TILE;
 	for (int i = t; i < KEY_TILE + 64; i += 256) {
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 		const i64 p = base + li;
 		if (p < n) {
 			u64 k = 0;
-			for (int d = 0; d < depth; d++) k = (k << bits) | sc[li + d];
+			for (int d = 0; d < depth; d++) k = k * radix + sc[li + d];
 			keys[p] = k;
 			vals[p] = (u32)p;
 		}
@@ -755,10 +763,10 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_symhist<<<hblocks, 256, 0, s>>>(d_T, n, b.meta); JP_LAUNCH(c);
 	k_fwd_codes<<<1, 256, 0, s>>>(b.meta); JP_LAUNCH(c);
 	JP_KCHECK();
-	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 3 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth
+	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 4 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth, key_bits
 	JP_CUDA(cudaStreamSynchronize(s));
-	const int bits = c.h_small[17], depth = c.h_small[18];
-	if (bits < 1 || bits > 9 || depth < 7 || depth > 64) { set_error_detail("symbol remap gave bits=%d depth=%d", bits, depth); return JP_ERR_INTERNAL; }
+	const int bits = c.h_small[17], depth = c.h_small[18], key_bits0 = c.h_small[19];
+	if (bits < 1 || bits > 9 || depth < 7 || depth > 63 || key_bits0 < 1 || key_bits0 > 63) { set_error_detail("symbol remap gave bits=%d depth=%d key bits=%d", bits, depth, key_bits0); return JP_ERR_INTERNAL; }
 	st->symbol_bits = bits; st->initial_depth = depth;
 
 	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0]); JP_LAUNCH(c);
@@ -767,7 +775,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
 	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
-	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, bits * depth, s, &c.launches);
+	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
