@@ -346,3 +346,49 @@ def test_consume_variant_and_trace(jp, orc, tmp_path):
     assert r.returncode == 0, r.stderr
     assert "[jp_bwt trace] forward: calls=1" in r.stderr and "[jp_bwt trace] inverse: calls=1" in r.stderr
     assert r.stderr.count("[jp_bwt call]") == 2
+
+
+def test_fuzz_small_blocks_against_oracle(jp, orc):
+    """Randomised differential test: many short blocks of random length, alphabet and structure (runs, repeats,
+    zero tails) through forward and inverse, bit-for-bit against the C restatement."""
+    rng = np.random.default_rng(20240607)
+    for case in range(300):
+        n = int(rng.integers(1, 6000)) if case % 7 else int(rng.integers(1, 5)) * 120
+        sigma = int(rng.choice([1, 2, 3, 4, 16, 64, 255, 256]))
+        T = rng.integers(0, sigma, n).astype(np.uint8)
+        kind = case % 5
+        if kind == 1 and n > 10:                       # long repeat
+            half = n // 2
+            T[half: 2 * half] = T[:half]
+        elif kind == 2:                                # runs
+            T = np.repeat(T[: max(1, n // 17)], 17)[:n]
+            n = T.size
+        elif kind == 3 and n > 40:                     # zero tail / zero island (sentinel vs 0x00)
+            T[-int(rng.integers(1, 40)):] = 0
+            T[n // 3: n // 3 + 9] = 0
+        elif kind == 4 and n > 300:                    # periodic with a defect
+            p = int(rng.integers(1, 40))
+            T = np.tile(T[:p], n // p + 1)[:n].copy()
+            T[n // 2] ^= 1
+        want = orc.forward(T, "port", prefill=0xEE)
+        got = jp.forward(T, prefill=0xEE)
+        assert (got == want).all(), (case, n, sigma, kind)
+        assert (jp.inverse(want) == T).all(), (case, n, sigma, kind)
+
+
+def test_maximum_block_size_round_trip(jp, orc):
+    """format.hpp:22 MAX_BLOCKSIZE = 1000 MiB: 32-bit indices, 31-bit ranks, byte offsets beyond 4 GiB in every table.
+    Too large for the CPU oracle to finish in seconds, so the size-independent properties are checked instead."""
+    n = 1000 * MiB
+    T = orc.gen("markov2", n, 31337)
+    out = jp.forward(T)
+    st = jp.last_stats()
+    nlen = n - n % 120
+    assert st.nlen == nlen and st.rounds >= 1
+    assert (np.bincount(out[:nlen], minlength=256) == np.bincount(T[:nlen], minlength=256)).all()
+    assert (out[nlen:n] == T[nlen:]).all()
+    I = orc.indices(out)
+    assert I.min() >= 1 and I.max() <= nlen and np.unique(I).size == 120
+    back = jp.inverse(out)
+    assert back.size == n and (back == T).all()
+    assert jp.last_stats().device_bytes <= 4 * nlen + nlen // 32 + (1 << 20)
