@@ -39,13 +39,49 @@ int map_dev_err(int de)
 	}
 }
 
+// ---- device memory accounting ---------------------------------------------------------------------------
+// Workspaces are per context and grow-only, so several large blocks in flight on one device (forward needs ~45N)
+// can exhaust it. Every allocation goes through dev_alloc: it honours the optional JP_BWT_DEVICE_MEM_LIMIT (bytes
+// the pool may hold per device) and turns a refused cudaMalloc into JP_ERR_OOM; the callers then make room
+// (relieve_memory_pressure) and retry instead of failing the block.
+static std::atomic<long long> g_dev_bytes[64];
+static long long mem_limit()
+{
+	static long long lim = -2;
+	if (lim == -2) { const char* e = getenv("JP_BWT_DEVICE_MEM_LIMIT"); lim = e ? atoll(e) : -1; }
+	return lim;
+}
+static int dev_alloc(int device, void** p, size_t bytes)
+{
+	const long long lim = mem_limit();
+	if (lim >= 0 && g_dev_bytes[device & 63].load() + (long long)bytes > lim) {
+		set_error_detail("device %d: %zu more bytes would exceed JP_BWT_DEVICE_MEM_LIMIT", device, bytes);
+		return JP_ERR_OOM;
+	}
+	const cudaError_t e = cudaMalloc(p, bytes);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		*p = nullptr;
+		set_error_detail("cudaMalloc(%zu) on device %d -> %s", bytes, device, cudaGetErrorString(e));
+		return e == cudaErrorMemoryAllocation ? JP_ERR_OOM : JP_ERR_CUDA;
+	}
+	g_dev_bytes[device & 63] += (long long)bytes;
+	return JP_OK;
+}
+static void dev_free(int device, void* p, size_t bytes)
+{
+	if (!p) return;
+	cudaFree(p);
+	g_dev_bytes[device & 63] -= (long long)bytes;
+}
+
 int arena_reserve(Ctx& c, size_t total)
 {
 	if (c.arena.cap - c.arena.off >= total) return JP_OK;
 	if (c.arena.off != 0) { set_error_detail("arena: %zu more bytes wanted with %zu live", total, c.arena.off); return JP_ERR_INTERNAL; }
-	if (c.arena.base) { JP_CUDA(cudaFree(c.arena.base)); c.arena.base = nullptr; c.arena.cap = 0; }
+	if (c.arena.base) { dev_free(c.device, c.arena.base, c.arena.cap); c.arena.base = nullptr; c.arena.cap = 0; }
 	const size_t want = (total + (64u << 20) - 1) & ~(size_t)((64u << 20) - 1);
-	JP_CUDA(cudaMalloc(&c.arena.base, want));
+	JP_TRY(dev_alloc(c.device, (void**)&c.arena.base, want));
 	c.arena.cap = want;
 	return JP_OK;
 }
@@ -255,13 +291,47 @@ static int ensure_io(Ctx& c, size_t bytes)
 {
 	bytes = Arena::align(bytes + 64);
 	if (c.d_io_cap >= bytes) return JP_OK;
-	if (c.d_in) { JP_CUDA(cudaFree(c.d_in)); c.d_in = nullptr; }
-	if (c.d_out) { JP_CUDA(cudaFree(c.d_out)); c.d_out = nullptr; }
+	dev_free(c.device, c.d_in, c.d_io_cap); c.d_in = nullptr;
+	dev_free(c.device, c.d_out, c.d_io_cap); c.d_out = nullptr;
 	c.d_io_cap = 0;
-	JP_CUDA(cudaMalloc(&c.d_in, bytes));
-	JP_CUDA(cudaMalloc(&c.d_out, bytes));
+	JP_TRY(dev_alloc(c.device, (void**)&c.d_in, bytes));
+	if (dev_alloc(c.device, (void**)&c.d_out, bytes) != JP_OK) { dev_free(c.device, c.d_in, bytes); c.d_in = nullptr; return JP_ERR_OOM; }
 	c.d_io_cap = bytes;
 	return JP_OK;
+}
+
+static void drop_memory(Ctx& c)
+{
+	dev_free(c.device, c.arena.base, c.arena.cap); c.arena.base = nullptr; c.arena.cap = 0; c.arena.off = 0;
+	dev_free(c.device, c.d_in, c.d_io_cap); c.d_in = nullptr;
+	dev_free(c.device, c.d_out, c.d_io_cap); c.d_out = nullptr;
+	c.d_io_cap = 0;
+}
+
+// A call on `self` ran out of device memory. Take the workspaces of idle contexts of the same device away; if
+// there are none, wait for a busy one to finish. false: nothing left to wait for -- the block really does not fit.
+static bool relieve_memory_pressure(Ctx& self)
+{
+	std::unique_lock<std::mutex> lk(g_pool.mu);
+	std::vector<Ctx*> idle;
+	bool others_busy = false;
+	for (auto& c : g_pool.ctxs) {
+		if (c.get() == &self || c->device != self.device) continue;
+		if (c->busy) others_busy = true;
+		else if (c->arena.base || c->d_in) { c->busy = true; idle.push_back(c.get()); }
+	}
+	if (!idle.empty()) {
+		lk.unlock();
+		for (Ctx* c : idle) drop_memory(*c);
+		lk.lock();
+		for (Ctx* c : idle) c->busy = false;
+		lk.unlock();
+		g_pool.cv.notify_all();
+		return true;
+	}
+	if (!others_busy && g_pool.pending[self.device] == 0) return false;
+	g_pool.cv.wait_for(lk, std::chrono::milliseconds(200));
+	return true;
 }
 
 static void begin_call(Ctx& c)
@@ -272,6 +342,8 @@ static void begin_call(Ctx& c)
 	memset(&t_stats, 0, sizeof(t_stats));
 	t_detail[0] = 0;
 }
+
+static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 len, i32 nlen, u8* out);
 
 static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_len)
 {
@@ -287,6 +359,24 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	JP_TRY(acquire(-1, &g.c));
 	const long long t_acquired = tr ? now_us() : 0;
 	Ctx& c = *g.c;
+	int rc = JP_ERR_OOM;
+	for (int attempt = 0; attempt < 256 && rc == JP_ERR_OOM; attempt++) {
+		if (attempt > 0 && !relieve_memory_pressure(c)) break;
+		rc = host_call_once(c, direction, in, in_len, len, nlen, out);
+	}
+	if (rc != JP_OK) return rc;
+	if (tr) {
+		const long long t_end = now_us();
+		trace_add(direction, len, t_begin, t_end, t_stats.ms_total + t_stats.ms_h2d + t_stats.ms_d2h);
+		if (g_trace_calls)
+			fprintf(stderr, "[jp_bwt call] dir=%d len=%d dev=%d t0_us=%lld wait_us=%lld call_us=%lld h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f\n", direction, len,
+			        c.device, t_begin, t_acquired - t_begin, t_end - t_begin, t_stats.ms_h2d, t_stats.ms_total, t_stats.ms_d2h);
+	}
+	return JP_OK;
+}
+
+static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 len, i32 nlen, u8* out)
+{
 	begin_call(c);
 	cudaStream_t s = c.own_stream;
 	JP_TRY(ensure_io(c, (size_t)len + JP_BWT_TRAILER_BYTES));
@@ -307,13 +397,6 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high;
-	if (tr) {
-		const long long t_end = now_us();
-		trace_add(direction, len, t_begin, t_end, t_stats.ms_total + t_stats.ms_h2d + t_stats.ms_d2h);
-		if (g_trace_calls)
-			fprintf(stderr, "[jp_bwt call] dir=%d len=%d dev=%d t0_us=%lld wait_us=%lld call_us=%lld h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f\n", direction, len,
-			        c.device, t_begin, t_acquired - t_begin, t_end - t_begin, t_stats.ms_h2d, t_stats.ms_total, t_stats.ms_d2h);
-	}
 	return JP_OK;
 }
 
@@ -325,10 +408,14 @@ static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int
 	CtxGuard g;
 	JP_TRY(acquire(device, &g.c));
 	Ctx& c = *g.c;
-	begin_call(c);
 	cudaStream_t s = stream ? (cudaStream_t)stream : c.own_stream;
-	int rc = direction == 0 ? forward_device(c, d_in, in_len, d_out, s, &t_stats)
-	                        : inverse_device(c, d_in, in_len, d_out, s, &t_stats, consume_in ? const_cast<u8*>(d_in) : nullptr);
+	int rc = JP_ERR_OOM;
+	for (int attempt = 0; attempt < 256 && rc == JP_ERR_OOM; attempt++) {
+		if (attempt > 0 && !relieve_memory_pressure(c)) break;
+		begin_call(c);
+		rc = direction == 0 ? forward_device(c, d_in, in_len, d_out, s, &t_stats)
+		                    : inverse_device(c, d_in, in_len, d_out, s, &t_stats, consume_in ? const_cast<u8*>(d_in) : nullptr);
+	}
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high;
 	return rc;

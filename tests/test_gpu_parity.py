@@ -392,3 +392,35 @@ def test_maximum_block_size_round_trip(jp, orc):
     back = jp.inverse(out)
     assert back.size == n and (back == T).all()
     assert jp.last_stats().device_bytes <= 4 * nlen + nlen // 32 + (1 << 20)
+
+
+def test_memory_pressure_degrades_concurrency_not_correctness(jp, orc):
+    """Workspaces are per context (forward ~45N). When several large blocks in flight do not fit the device (or
+    JP_BWT_DEVICE_MEM_LIMIT), callers take idle contexts' workspaces or wait for a busy one -- no block fails; a
+    block that cannot fit at all returns JP_ERR_OOM cleanly."""
+    code = r'''
+import sys, threading, numpy as np
+sys.path.insert(0, %r)
+import jampack_b200 as jp, synth
+blocks = [synth.gen("markov2", (16 << 20) + 120 * i, 60 + i) for i in range(6)]
+outs, errs = [None] * 6, []
+def work(i):
+    try:
+        f = jp.forward(blocks[i]); outs[i] = (synth.fnv(f), bool((jp.inverse(f) == blocks[i]).all()))
+    except Exception as e: errs.append(repr(e))
+th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+[t.start() for t in th]; [t.join() for t in th]
+print("ERRS", errs); print("OUTS", outs)
+''' % ROOT
+    env = dict(os.environ, JP_BWT_DEVICE_MEM_LIMIT=str(2_000_000_000))
+    r = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "ERRS []" in r.stdout, r.stdout
+    want = [(orc.fnv(orc.forward(orc.gen("markov2", (16 << 20) + 120 * i, 60 + i), _impl(orc))), True) for i in range(6)]
+    assert ("OUTS " + repr(want)) in r.stdout, r.stdout
+    code2 = ("import numpy as np, jampack_b200 as jp\n"
+             "try:\n    jp.forward(np.zeros(16 << 20, dtype=np.uint8)); print('NOERR')\n"
+             "except jp.BwtError as e:\n    print('RC', e.rc)\n")
+    r = subprocess.run([os.sys.executable, "-c", code2], cwd=ROOT, env=dict(os.environ, JP_BWT_DEVICE_MEM_LIMIT=str(300_000_000)),
+                       capture_output=True, text=True, timeout=300)
+    assert "RC -4" in r.stdout, r.stdout + r.stderr
