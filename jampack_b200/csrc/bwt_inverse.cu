@@ -24,6 +24,7 @@
 // Device memory: caller's in (N+480) + out (N) + lf (4N) = 6N, plus o(N): 8 B per sub-chain (N/8 at m = 64)
 // and 1 KiB per 64 KiB tile (N/64).
 #include "bwt_internal.cuh"
+#include <algorithm>
 
 namespace jp {
 
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restr
 // start lies the start of `next`"; replacing it by (next.next, dist + next.dist) keeps that true whichever
 // version of next's record was read, so no double buffering or rounds are needed: 8-byte loads/stores are
 // single transactions. Anchors (ids >= S) absorb.
-__global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int check_units)
+__global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int check_units, int hop_cap)
 {
 	const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
 	const u32 nodes = S + N_ANCHOR;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, 
 		const u64 o = vrec[nxt];
 		nxt = (u32)(o >> 32);
 		dist += (u32)o;
-		if (nxt == REC_INVALID || ++hops > RANK_HOP_CAP) { dev_fail(err, DE_RANK_LOOP); nxt = S; dist = 0; break; }
+		if (nxt == REC_INVALID || ++hops > hop_cap) { dev_fail(err, DE_RANK_LOOP); nxt = S; dist = 0; break; }
 		vrec[id] = pack_rec(nxt, dist);
 	}
 	vrec[id] = pack_rec(nxt, dist);
@@ -589,7 +590,10 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	// (a two-level scheme -- majors walk to majors, jump, hand down -- was tried: 0.86 ms against 0.28 ms; the
 	// dependent record-to-record walks are latency-bound, the flat jumping is not)
-	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, 1); JP_LAUNCH(c);
+	// a decode unit holds about nodes/120 sub-chains, so no honest list is longer than a few times that; the cap
+	// only bounds the time spent on a corrupt block whose records form cycles
+	const int hop_cap = (int)std::min<u64>((u64)RANK_HOP_CAP, (u64)nodes / 16 + 4096);
+	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, 1, hop_cap); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[4], s));
 	JP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nlen, s));               // shared words of neighbouring sub-chains are merged by RED.OR

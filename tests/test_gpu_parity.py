@@ -424,3 +424,33 @@ print("ERRS", errs); print("OUTS", outs)
     r = subprocess.run([os.sys.executable, "-c", code2], cwd=ROOT, env=dict(os.environ, JP_BWT_DEVICE_MEM_LIMIT=str(300_000_000)),
                        capture_output=True, text=True, timeout=300)
     assert "RC -4" in r.stdout, r.stdout + r.stderr
+
+
+def test_corrupted_bwt_bytes_never_hang_or_crash(jp, orc):
+    """Flipping bytes in the BWT body breaks the single LF cycle into arbitrary cycles. The decoder must come back
+    quickly with an error (or, when the damage happens to leave a consistent permutation, with some block of the
+    right size) -- never hang, never read out of bounds; the container's checksum (jampack.cpp:56-57) does the rest."""
+    import time
+    rng = np.random.default_rng(99)
+    T = orc.gen("markov2", MiB, 13)
+    B = orc.forward(T, _impl(orc))
+    n = T.size
+    outcomes = {"error": 0, "output": 0}
+    t0 = time.time()
+    for trial in range(24):
+        bad = B.copy()
+        k = int(rng.integers(1, 50)) if trial % 3 else 1
+        pos = rng.integers(0, n - n % 120, k)
+        bad[pos] = rng.integers(0, 256, k).astype(np.uint8)
+        if trial % 4 == 3:
+            bad[: n // 2] = bad[n // 2: n // 2 * 2]            # wholesale damage
+        try:
+            out = jp.inverse(bad)
+            assert out.size == n
+            outcomes["output"] += 1
+        except jp.BwtError as e:
+            assert e.rc in (-5, -6), e
+            outcomes["error"] += 1
+    assert time.time() - t0 < 60
+    assert outcomes["error"] > 0
+    assert (jp.inverse(B) == T).all()
