@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, 
 		if (j < A) { v[i] = __ldcs(V + j); r[i] = __ldcs(R + j); }
 	}
 	#pragma unroll
-	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (v[i] >> region_log2) == region) ISA[v[i]] = r[i];
+	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (region_log2 >= 32 || (v[i] >> region_log2) == region)) ISA[v[i]] = r[i];
 }
 
 // ---- 5a. doubling round, small groups: gather + segmented sort in shared memory -------------------------
@@ -742,7 +742,17 @@ static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos,
 	if (staged) {
 		const u32 n_entries = c.cur_n + 1, regions = (n_entries + (1u << b.isa_region_log2) - 1) >> b.isa_region_log2;
 		const u32 stiles = (A + 2047) / 2048;
-		k_isa_scatter<<<regions * stiles, 256, 0, s>>>(b.rb.v[cur], b.R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
+		if (regions <= 4 || regions > 256) {
+			// few regions: stream the slots once per region and keep the ranks that fall in it
+			k_isa_scatter<<<regions * stiles, 256, 0, s>>>(b.rb.v[cur], b.R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
+		} else {
+			// many regions (blocks over 64 MiB): one radix partition pass buckets the (suffix, rank) pairs by region -- the
+			// sorted keys of this step are dead, their buffer holds the bucketed pairs -- then a single ordered sweep
+			u32* pv = reinterpret_cast<u32*>(b.rb.k[cur]);
+			u32* pr = pv + A;
+			if (radix_partition_u32(b.rb.v[cur], b.R, pv, pr, A, b.isa_region_log2, b.rb.tile_hist, b.rb.totals, s, &c.launches) != 0) { set_error_detail("radix partition setup failed"); return JP_ERR_CUDA; }
+			k_isa_scatter<<<stiles, 256, 0, s>>>(pv, pr, A, b.ISA, 32, stiles); JP_LAUNCH(c);
+		}
 	}
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 8, b.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));

@@ -18,13 +18,15 @@ constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per block
 constexpr size_t RS_SMEM_SCATTER = (size_t)RS_TILE * (8 + 4);
 
 __device__ __forceinline__ u32 rs_digit(u64 k, int shift) { return (u32)(k >> shift) & 255u; }
+__device__ __forceinline__ u32 rs_digit(u32 k, int shift) { return (k >> shift) & 255u; }
 
 // Histogram layout is digit-major, tile_hist[digit * stride + tile] (stride = tiles rounded up to 4), so that
 // the per-digit scan over tiles reads and writes whole rows (the tile-major layout made that scan as
 // expensive as the scatter itself: 0.31 ms per pass at 16 K tiles, ncu round 1).
 __host__ __device__ __forceinline__ u32 rs_stride(u32 tiles) { return (tiles + 3u) & ~3u; }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ tile_hist, u32 stride)
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ keys, u32 n, int shift, u32* __restrict__ tile_hist, u32 stride)
 {
 	__shared__ u32 h[RS_WARPS][256];
 	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -92,13 +94,14 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 #ifndef RS_SCATTER_MIN_BLOCKS
 #define RS_SCATTER_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin,
-                                                           u64* __restrict__ kout, u32* __restrict__ vout,
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const K* __restrict__ kin, const u32* __restrict__ vin,
+                                                           K* __restrict__ kout, u32* __restrict__ vout,
                                                            const u32* __restrict__ tile_off, u32 stride, u32 n, int shift)
 {
 	extern __shared__ __align__(16) u8 rs_smem[];
-	u64* skey = reinterpret_cast<u64*>(rs_smem);
-	u32* sval = reinterpret_cast<u32*>(rs_smem + (size_t)RS_TILE * 8);
+	K* skey = reinterpret_cast<K*>(rs_smem);
+	u32* sval = reinterpret_cast<u32*>(rs_smem + (size_t)RS_TILE * sizeof(K));
 	__shared__ u32 wcnt[RS_WARPS][256];
 	__shared__ u32 bin_start[256];
 	__shared__ u32 g_off[256];
@@ -110,14 +113,14 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 	const u32 valid = min((u32)RS_TILE, n - tile_base);
 	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
 
-	u64 key[RS_ITEMS];
+	K key[RS_ITEMS];
 	u32 val[RS_ITEMS];
 	const u32 wbase = tile_base + w * (32 * RS_ITEMS);
 	#pragma unroll
 	for (int i = 0; i < RS_ITEMS; i++) {
 		const u32 p = wbase + i * 32 + lane;
 		const bool ok = p < n;
-		key[i] = ok ? kin[p] : ~0ull;     // padding sorts last inside the tile and is never written out
+		key[i] = ok ? kin[p] : (K)~(K)0;  // padding sorts last inside the tile and is never written out
 		val[i] = ok ? vin[p] : 0u;
 	}
 	__syncthreads();
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 	__syncthreads();
 
 	for (u32 j = t; j < valid; j += RS_THREADS) {
-		const u64 k = skey[j];
+		const K k = skey[j];
 		const u32 dst = g_off[rs_digit(k, shift)] + j;
 		kout[dst] = k;
 		vout[dst] = sval[j];
@@ -324,7 +327,7 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 {
 	if (n == 0) return cur;
 	// function attributes are per device; setting one is a host-only call
-	if (cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
+	if (cudaFuncSetAttribute(k_rs_scatter<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
 	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
 	if (!b.classic && n < (1u << 30)) {
 		if (cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
@@ -347,14 +350,31 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 		return cur;
 	}
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		k_rs_hist<<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride);
+		k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride);
 		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
 		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
-		k_rs_scatter<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift);
+		k_rs_scatter<u64><<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift);
 		*launches += 4;
 		cur ^= 1;
 	}
 	return cur;
+}
+
+// One stable 8-bit partition pass over (32-bit key, 32-bit value) pairs: (kin, vin) -> (kout, vout) ordered by
+// digit (key >> shift) & 255. Used to bucket (suffix, rank) pairs by ISA region before they are scattered.
+inline int radix_partition_u32(const u32* kin, const u32* vin, u32* kout, u32* vout, u32 n, int shift,
+                               u32* tile_hist, u32* totals, cudaStream_t s, int* launches)
+{
+	if (n == 0) return 0;
+	const size_t smem = (size_t)RS_TILE * (4 + 4);
+	if (cudaFuncSetAttribute(k_rs_scatter<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
+	k_rs_hist<u32><<<tiles, RS_THREADS, 0, s>>>(kin, n, shift, tile_hist, stride);
+	k_rs_totals<<<256, 256, 0, s>>>(tile_hist, tiles, stride, totals);
+	k_rs_scan<<<256, 256, 0, s>>>(tile_hist, tiles, stride, totals);
+	k_rs_scatter<u32><<<tiles, RS_THREADS, smem, s>>>(kin, vin, kout, vout, tile_hist, stride, n, shift);
+	*launches += 4;
+	return 0;
 }
 
 } // namespace jp
