@@ -296,7 +296,7 @@ constexpr int SG_ITEMS   = 16;
 constexpr int SG_CAP     = SG_THREADS * SG_ITEMS;   // 4096 elements sorted per block
 constexpr int SG_WIN     = SG_CAP / 2;              // window of group heads per block
 constexpr size_t SG_SMEM = (size_t)SG_CAP * (8 + 4);
-constexpr u32 SG_PAIR_MAX = 256;                    // longest group the all-pairs rank refinement takes on
+constexpr u32 SG_PAIR_MAX = 1024;                    // longest group the all-pairs rank refinement takes on
 
 struct SegTile { u32 start, len; };
 
