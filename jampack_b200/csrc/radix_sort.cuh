@@ -171,9 +171,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 // The three-kernel pass above reads the keys twice (histogram, scatter). Here one kernel does a whole digit:
 // blocks take tiles in ticket order, rank their keys, publish the tile's digit counts as an AGGREGATE word,
 // sum their predecessors' words backwards until they meet an inclusive PREFIX word, publish their own prefix
-// and scatter. The digit's global histogram (which does not depend on the order of the keys) comes from the
-// previous pass, which counts the next digit while it has the keys in registers; only the first pass needs a
-// counting kernel. A tile's predecessors hold earlier tickets, so they are running or done and publish before
+// and scatter. The global histogram of every digit position (which does not depend on the order of the keys) is
+// counted once, up front, in a single read of the keys (k_os_count_all). A tile's predecessors hold earlier tickets, so they are running or done and publish before
 // they wait: the chain cannot deadlock; a spin cap turns any surprise into an error flag instead of a hang.
 constexpr u32 OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 1u << 31, OS_VALUE_MASK = (1u << 30) - 1;
 constexpr u32 OS_SPIN_CAP = 1u << 26;
@@ -181,34 +180,37 @@ constexpr u32 OS_SPIN_CAP = 1u << 26;
 __device__ __forceinline__ void os_store(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 os_load(const u32* p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-// global digit counts of one digit position (first pass only)
-__global__ void __launch_bounds__(RS_THREADS) k_os_count(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ ghist)
+// global digit counts of EVERY digit position in one read of the keys: ghist[pass][256]
+constexpr int OS_MAX_PASSES = 8;
+__global__ void __launch_bounds__(RS_THREADS) k_os_count_all(const u64* __restrict__ keys, u32 n, int bit_lo, int passes, u32* __restrict__ ghist)
 {
-	__shared__ u32 h[RS_WARPS][256];
+	__shared__ u32 h[OS_MAX_PASSES][256];
 	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
+	for (int i = t; i < OS_MAX_PASSES * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
 	__syncthreads();
-	u32* hw = h[w];
+	const u32 lt = lanemask_lt();
 	for (u32 tile = blockIdx.x; (u64)tile * RS_TILE < n; tile += gridDim.x) {
 		const u32 base = tile * RS_TILE + w * (32 * RS_ITEMS);
-		#pragma unroll
+		#pragma unroll 4
 		for (int i = 0; i < RS_ITEMS; i++) {
 			const u32 p = base + i * 32 + lane;
-			const u32 d = p < n ? rs_digit(keys[p], shift) : 256u;
-			const u32 peers = __match_any_sync(0xffffffffu, d);
-			if (d < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+			const bool ok = p < n;
+			const u64 k = ok ? keys[p] : 0ull;
+			const u32 vmask = __ballot_sync(0xffffffffu, ok);
+			for (int q = 0; q < passes; q++) {
+				const u32 d = rs_digit(k, bit_lo + 8 * q);
+				const u32 peers = match_any8_adaptive(d) & vmask;
+				if (ok && (peers & lt) == 0) atomicAdd(&h[q][d], (u32)__popc(peers));
+			}
 		}
 	}
 	__syncthreads();
-	u32 s = 0;
-	#pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
-	if (s) atomicAdd(&ghist[t], s);
+	for (int q = 0; q < passes; q++) { const u32 c = h[q][t]; if (c) atomicAdd(&ghist[q * 256 + t], c); }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ kin, const u32* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_os_pass(const u64* __restrict__ kin, const u32* __restrict__ vin,
                                                         u64* __restrict__ kout, u32* __restrict__ vout, u32 n, int shift,
-                                                        const u32* __restrict__ ghist, u32* __restrict__ ghist_next, int next_shift,
+                                                        const u32* __restrict__ ghist,
                                                         u32* __restrict__ lookback, u32* __restrict__ ticket, int* __restrict__ err)
 {
 	extern __shared__ __align__(16) u8 rs_smem[];
@@ -217,7 +219,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ 
 	__shared__ u32 wcnt[RS_WARPS][256];
 	__shared__ u32 bin_start[256];
 	__shared__ u32 g_off[256];
-	__shared__ u32 nhist[256];
 	__shared__ u32 ws[32];
 	__shared__ u32 s_tile;
 
@@ -225,7 +226,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ 
 	const u32 lt = lanemask_lt();
 	if (t == 0) s_tile = atomicAdd(ticket, 1u);
 	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
-	nhist[t] = 0;
 	__syncthreads();
 	const u32 tile = s_tile;
 	const u32 tile_base = tile * RS_TILE;
@@ -253,15 +253,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ 
 		before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
 		rank[i] = before + below;
 		__syncwarp();
-	}
-	if (ghist_next) {                                   // count the next digit while the keys are here
-		#pragma unroll
-		for (int i = 0; i < RS_ITEMS; i++) {
-			const bool ok = wbase + i * 32 + lane < n;
-			const u32 d = ok ? rs_digit(key[i], next_shift) : 256u;
-			const u32 peers = __match_any_sync(0xffffffffu, d);
-			if (ok && (peers & lt) == 0) atomicAdd(&nhist[d], (u32)__popc(peers));
-		}
 	}
 	__syncthreads();
 
@@ -291,7 +282,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const u64* __restrict__ 
 	const u32 inc = block_incl_sum(run, ws, &total);
 	bin_start[t] = inc - run;
 	g_off[t] = (dig_incl - ghist[t]) + excl - (inc - run);
-	if (ghist_next && nhist[t]) atomicAdd(&ghist_next[t], nhist[t]);
 	__syncthreads();
 
 	#pragma unroll
@@ -314,7 +304,7 @@ struct RadixBuffers {
 	u64* k[2]; u32* v[2];
 	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries; the look-back words of the one-sweep passes
 	u32* totals;      // 256
-	u32* os_state;    // 1024: digit histograms of the current / next pass [0..512), ticket [512]
+	u32* os_state;    // one-sweep: digit histograms of every pass [8][256], then the tile ticket
 	int* err;
 	bool classic;     // three-kernel passes (A/B switch, and blocks of 2^30 keys or more)
 };
@@ -331,21 +321,20 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
 	if (!b.classic && n < (1u << 30)) {
 		if (cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
-		u32* gh[2] = {b.os_state, b.os_state + 256};
-		u32* ticket = b.os_state + 512;
-		cudaMemsetAsync(b.os_state, 0, 1024 * sizeof(u32), s);
-		k_os_count<<<min(tiles, 148u * 8u), RS_THREADS, 0, s>>>(b.k[cur], n, bit_lo, gh[0]);
+		const int passes = (bit_hi - bit_lo + 7) / 8;
+		if (passes > OS_MAX_PASSES) return -1;
+		u32* ghist = b.os_state;                        // [passes][256]
+		u32* ticket = b.os_state + OS_MAX_PASSES * 256;
+		cudaMemsetAsync(b.os_state, 0, (OS_MAX_PASSES * 256 + 16) * sizeof(u32), s);
+		k_os_count_all<<<min(tiles, 148u * 8u), RS_THREADS, 0, s>>>(b.k[cur], n, bit_lo, passes, ghist);
 		*launches += 1;
-		int g = 0;
-		for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-			const bool more = shift + 8 < bit_hi;
+		for (int q = 0; q < passes; q++) {
 			cudaMemsetAsync(b.tile_hist, 0, (size_t)tiles * 256 * sizeof(u32), s);
-			cudaMemsetAsync(gh[g ^ 1], 0, 256 * sizeof(u32), s);
 			cudaMemsetAsync(ticket, 0, sizeof(u32), s);
-			k_os_pass<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n, shift, gh[g],
-			                                                     more ? gh[g ^ 1] : nullptr, shift + 8, b.tile_hist, ticket, b.err);
+			k_os_pass<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n, bit_lo + 8 * q,
+			                                                     ghist + q * 256, b.tile_hist, ticket, b.err);
 			*launches += 1;
-			cur ^= 1; g ^= 1;
+			cur ^= 1;
 		}
 		return cur;
 	}
