@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_inv_ctable(const u32* __restrict__ bin_
 // coalesced 128 B rows of 32-bit words and re-distributed by shuffle so that lane l handles byte
 // 32*k + l of the row (text order == lane order). Equal bytes inside a warp step are ranked with
 // match.any; running per-warp counters live in shared memory; LF values leave as 128 B coalesced rows.
-__global__ void __launch_bounds__(INV_THREADS) k_inv_lf(const u8* __restrict__ bwt, i32 n,
+__global__ void __launch_bounds__(INV_THREADS, 3) k_inv_lf(const u8* __restrict__ bwt, i32 n,
                                                         const u32* __restrict__ tile_excl, const InvMeta* __restrict__ meta,
                                                         u32* __restrict__ lf, int log2m)
 {
