@@ -362,7 +362,7 @@ __device__ __forceinline__ u32 warp_rev_incl_min(u32 v)
 // scans (last head at or before me / first group end at or after me) stitched across the block through a small
 // table with a single barrier; then it counts the members of its group that sort before it.
 constexpr size_t SG_SMEM_LIGHT = (size_t)SG_CAP * (4 + 4 + 1);
-__global__ void __launch_bounds__(SG_THREADS, 4) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
+__global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
                                                          const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
                                                          u8* __restrict__ F, u32* __restrict__ counters /*[2]=has_large [3]=queued*/,
                                                          u32* __restrict__ queue, u32* __restrict__ win_first, u32* __restrict__ win_large,
