@@ -18,6 +18,7 @@
 //                     indices ISA[k*step] (bwt.cpp:44-48,57-61), the raw tail (bwt.cpp:32-33).
 #include "bwt_internal.cuh"
 #include "radix_sort.cuh"
+#include <chrono>
 
 namespace jp {
 
@@ -801,6 +802,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	i64 h = depth;
 	int rounds = 0;
 	double large_frac_prev = 0.0;
+	const bool trace_rounds = getenv("JP_BWT_TRACE_ROUNDS") != nullptr;      // one stderr line per doubling round (host wall time)
+	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	while (A > 0) {
 		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
@@ -858,6 +861,12 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
 			if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 			JP_TRY(group_step(c, b, cur, pc, false, false, A, rank_bits, s));
+		}
+		if (trace_rounds) {
+			const double t1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+			fprintf(stderr, "[jp_bwt round] %d h=%lld active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h, A, G,
+			        (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
+			t_round = t1;
 		}
 		act = cur ^ 1; pc ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
