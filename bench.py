@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true")
+    ap.add_argument("--callers", type=int, default=4, help="blocks in flight per GPU (the library keeps up to JP_BWT_MAX_CTX=4 contexts per device)")
     return ap.parse_args()
 
 
@@ -346,7 +347,7 @@ def main():
     h_in.array[:] = B
     inv_e2e_ms = timed_host(lambda: jp.inverse(h_in.array, out=h_out.array))
     parity["round_trip"] = parity["round_trip"] and bool((h_out.array[:n] == T).all())
-    CALLERS = 4
+    CALLERS = args.callers
     inv_e2e_c_ms, okc = timed_host_concurrent("inverse", CALLERS)
     parity["round_trip"] = parity["round_trip"] and okc
     inv_c_ms, okc, inv_c_launches = timed_device_concurrent("inverse", CALLERS)

@@ -133,7 +133,14 @@ static void trace_add(int direction, long long bytes, long long t0, long long t1
 }
 
 // ---- context pool -----------------------------------------------------------------------------------
-static const int MAX_CTX_PER_DEVICE = 4;
+// blocks in flight per device; more hides more latency but multiplies the workspaces (JP_BWT_MAX_CTX to override)
+static int max_ctx_per_device()
+{
+	static int v = 0;
+	if (v == 0) { const char* e = getenv("JP_BWT_MAX_CTX"); v = e ? atoi(e) : 4; if (v < 1) v = 1; if (v > 32) v = 32; }
+	return v;
+}
+#define MAX_CTX_PER_DEVICE max_ctx_per_device()
 
 struct Pool {
 	std::mutex mu;
