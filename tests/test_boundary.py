@@ -83,3 +83,23 @@ def test_product_does_not_import_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                     text = open(os.path.join(dp, f), errors="ignore").read()
                     assert "oracle" not in text.lower() or f == "bwt_shim.cpp", os.path.join(dp, f)
+
+
+def test_host_shims_compile_standalone(tmp_path):
+    """The C++ host side a Jampack maintainer links: both shims build without the reference's headers
+    (-DJP_STANDALONE_STAGE uses jampack_b200/host/jp_stage.hpp) and define exactly the reference's symbols."""
+    import subprocess
+    host = os.path.join(ROOT, "jampack_b200", "host")
+    objs = []
+    for src, extra in (("bwt_shim.cpp", ["-DJP_STANDALONE_STAGE"]), ("divsufsort_shim.cpp", [])):
+        obj = tmp_path / (src + ".o")
+        subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-c", os.path.join(host, src), "-I", host,
+                        "-I", os.path.join(ROOT, "include"), "-o", str(obj)] + extra, check=True)
+        objs.append(str(obj))
+    syms = subprocess.run(["nm", "-C", "--defined-only"] + objs, capture_output=True, text=True, check=True).stdout
+    assert "BlockSort::Bwt::ForwardBwt(Buffer, Buffer)" in syms
+    assert "BlockSort::Bwt::InverseBwt(Buffer, Buffer, Options)" in syms
+    assert " T divsufsort" in syms
+    und = subprocess.run(["nm", "-u"] + objs, capture_output=True, text=True, check=True).stdout
+    for s in ("jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_suffix_array", "jp_bwt_strerror"):
+        assert s in und
