@@ -75,14 +75,19 @@ __global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
 }
 
 // ---- 2. initial keys -------------------------------------------------------------------------------
-constexpr int KEY_TILE = 2048;
+// One block builds the keys of one radix tile (RS_TILE positions) and, having them in hand, also counts the
+// lowest digit: the first radix pass starts from this tile histogram instead of re-reading the keys.
+constexpr int KEY_TILE = RS_TILE;
 __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 n, const FwdMeta* __restrict__ meta,
-                                                  u64* __restrict__ keys, u32* __restrict__ vals)
+                                                  u64* __restrict__ keys, u32* __restrict__ vals,
+                                                  u32* __restrict__ tile_hist, u32 stride)
 {
 	__shared__ u16 sc[KEY_TILE + 64];
 	__shared__ u16 code[256];
-	const int t = threadIdx.x;
+	__shared__ u32 h[8][256];
+	const int t = threadIdx.x, w = t >> 5;
 	code[t] = (u16)meta->code[t];
+	for (int i = t; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
 	const int depth = meta->depth;
 	const u64 radix = (u64)meta->sigma + 1;
 	__syncthreads();
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 		sc[i] = p < n ? code[T[p]] : (u16)0;
 	}
 	__syncthreads();
-	#pragma unroll
+	#pragma unroll 4
 	for (int j = 0; j < KEY_TILE / 256; j++) {
 		const int li = j * 256 + t;
 		const i64 p = base + li;
@@ -101,8 +106,14 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 			for (int d = 0; d < depth; d++) k = k * radix + sc[li + d];
 			keys[p] = k;
 			vals[p] = (u32)p;
+			atomicAdd(&h[w][(u32)k & 255u], 1u);           // low digits of text-order keys are spread: lanes rarely collide
 		}
 	}
+	__syncthreads();
+	u32 sum = 0;
+	#pragma unroll
+	for (int k = 0; k < 8; k++) sum += h[k][t];
+	tile_hist[(size_t)t * stride + blockIdx.x] = sum;
 }
 
 // ---- 4/5. group heads -> ranks, retire singletons, compact the rest ----------------------------------
@@ -781,13 +792,14 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	if (bits < 1 || bits > 9 || depth < 7 || depth > 63 || key_bits0 < 1 || key_bits0 > 63) { set_error_detail("symbol remap gave bits=%d depth=%d key bits=%d", bits, depth, key_bits0); return JP_ERR_INTERNAL; }
 	st->symbol_bits = bits; st->initial_depth = depth;
 
-	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0]); JP_LAUNCH(c);
+	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
+	                                                         rs_stride((u32)radix_tiles((size_t)n))); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
 	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
-	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches);
+	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/true);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));

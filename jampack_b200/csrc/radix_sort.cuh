@@ -40,8 +40,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ ke
 		// keys of neighbouring suffixes often share a digit: aggregate inside the warp before the atomic
 		const bool ok = p < n;
 		const u32 d = ok ? rs_digit(keys[p], shift) : 0u;
-		const u32 peers = match_any8_adaptive(d) & __ballot_sync(0xffffffffu, ok);
-		if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+		// few distinct digits in the warp: aggregate with match.any and add once per digit; many: one shared atomic
+		// per lane (hardly any two lanes collide, and neither match.any nor eight ballots is cheaper than that)
+		const u32 prev = __shfl_up_sync(0xffffffffu, d, 1);
+		const u32 boundaries = __popc(__ballot_sync(0xffffffffu, d != prev));
+		if (boundaries <= 24) {
+			const u32 peers = __match_any_sync(0xffffffffu, d) & __ballot_sync(0xffffffffu, ok);
+			if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&hw[d], (u32)__popc(peers));
+		} else if (ok) atomicAdd(&hw[d], 1u);
 	}
 	__syncthreads();
 	u32 s = 0;
@@ -313,7 +319,9 @@ inline size_t radix_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
 // Sorts pairs in (k[cur], v[cur]) by key bits [bit_lo, bit_hi); returns the index (0/1) of the buffers
 // holding the result, or a negative error code. launches is incremented per kernel.
-inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit_hi, cudaStream_t s, int* launches)
+// first_hist_ready: b.tile_hist already holds the tile histogram of the first digit (the producer of the keys made it)
+inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit_hi, cudaStream_t s, int* launches,
+                            bool first_hist_ready = false)
 {
 	if (n == 0) return cur;
 	// function attributes are per device; setting one is a host-only call
@@ -339,11 +347,11 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 		return cur;
 	}
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride);
+		if (!(first_hist_ready && shift == bit_lo)) { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
 		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
 		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
 		k_rs_scatter<u64><<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift);
-		*launches += 4;
+		*launches += 3;
 		cur ^= 1;
 	}
 	return cur;
