@@ -64,7 +64,7 @@ int jp_bwt_forward(const uint8_t* in, int32_t len, uint8_t* out, int32_t* out_le
 int jp_bwt_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, int32_t* out_len);
 
 /* ---- the same stage with the block already resident in HBM ---------------------------------------
- * d_in / d_out are device pointers on `device` (d_out at least 4-byte aligned). The work is enqueued on
+ * d_in / d_out are device pointers on `device`, both 16-byte aligned. The work is enqueued on
  * `stream` (a cudaStream_t, or NULL for the context's own stream) and the call returns after that stream
  * has drained. These are what the `value` leg of bench.py times, and what a device-resident
  * neighbour stage would call. */
