@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
                                                   u32* __restrict__ tile_hist, u32 stride)
 {
 	__shared__ u16 sc[KEY_TILE + 64];
+	__shared__ u32 part[KEY_TILE + 32];       // value of the q = depth/2 symbols starting at each position (fits 32 bits)
 	__shared__ u16 code[256];
 	__shared__ u32 h[8][256];
 	const int t = threadIdx.x, w = t >> 5;
 	code[t] = (u16)meta->code[t];
 	for (int i = t; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
-	const int depth = meta->depth;
-	const u64 radix = (u64)meta->sigma + 1;
+	const int depth = meta->depth, q = depth >> 1;
+	const u32 radix = (u32)meta->sigma + 1;
 	__syncthreads();
 	const i64 base = (i64)blockIdx.x * KEY_TILE;
 	for (int i = t; i < KEY_TILE + 64; i += 256) {
@@ -97,13 +98,24 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 		sc[i] = p < n ? code[T[p]] : (u16)0;
 	}
 	__syncthreads();
+	// key(i) = part(i) * radix^(depth-q) + [part(i+q) or part(i+q) * radix + symbol(i+2q)]: q 32-bit multiply-adds per
+	// position and one or two 64-bit ones, instead of `depth` 64-bit multiply-adds
+	for (int i = t; i < KEY_TILE + 32; i += 256) {
+		u32 v = 0;
+		for (int d = 0; d < q; d++) v = v * radix + sc[i + d];
+		part[i] = v;
+	}
+	u64 hi_scale = 1;
+	for (int d = 0; d < depth - q; d++) hi_scale *= radix;
+	__syncthreads();
 	#pragma unroll 4
 	for (int j = 0; j < KEY_TILE / 256; j++) {
 		const int li = j * 256 + t;
 		const i64 p = base + li;
 		if (p < n) {
-			u64 k = 0;
-			for (int d = 0; d < depth; d++) k = k * radix + sc[li + d];
+			u64 tail = part[li + q];
+			if (depth & 1) tail = tail * radix + sc[li + 2 * q];
+			const u64 k = (u64)part[li] * hi_scale + tail;
 			keys[p] = k;
 			vals[p] = (u32)p;
 			atomicAdd(&h[w][(u32)k & 255u], 1u);           // low digits of text-order keys are spread: lanes rarely collide
