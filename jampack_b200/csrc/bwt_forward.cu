@@ -724,7 +724,7 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	const size_t N = (size_t)n;
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
 	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + 2 * Arena::align(N * 4) +
-	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) + Arena::align(gtiles * sizeof(GAgg)) +
+	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) + Arena::align(N + 64) + Arena::align(gtiles * sizeof(GAgg)) +
 	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + 5 * Arena::align((N / SG_WIN + 16) * 4);
 	JP_TRY(arena_reserve(c, total));
 	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
@@ -736,6 +736,7 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	b.rb.tile_hist = arena_take<u32>(c, (rtiles + 4) * 256);
 	b.rb.totals = arena_take<u32>(c, 256);
 	b.rb.os_state = arena_take<u32>(c, 8 * 256 + 64);
+	b.rb.dnext = getenv("JP_BWT_RADIX_NO_DIGIT_BYTES") ? nullptr : arena_take<u8>(c, N + 64);
 	// Measured on B200 (64 M pairs, 8 passes): three-kernel passes 5.07 ms, one-sweep (all digits counted in one read of
 	// the keys + 8 look-back passes) 6.18 ms -- with ~440 tiles in flight the per-digit look-back chain costs more than
 	// the key re-read it saves, so the classic pass is the default.

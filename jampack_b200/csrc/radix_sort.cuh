@@ -56,6 +56,38 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ ke
 	tile_hist[(size_t)t * stride + blockIdx.x] = s;
 }
 
+// The same tile histogram from a one-byte-per-key digit array. Every scatter pass leaves such an array for the NEXT
+// digit next to the pairs it writes (1 extra byte per pair), so the histogram of passes 2.. reads 1 byte per key
+// instead of 8 (ncu: k_rs_hist was DRAM-bound on the 8-byte keys, 0.18-0.21 ms per 64 M keys).
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist_bytes(const u8* __restrict__ digits, u32 n, u32* __restrict__ tile_hist, u32 stride)
+{
+	__shared__ u32 h[RS_WARPS][256];
+	const int t = threadIdx.x, w = t >> 5;
+	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
+	__syncthreads();
+	u32* hw = h[w];
+	const u32 p = blockIdx.x * RS_TILE + t * 16;        // RS_TILE = RS_THREADS * 16: one 16-byte load per thread
+	if (p + 16 <= n) {
+		const uint4 q = *reinterpret_cast<const uint4*>(digits + p);
+		const u32 wd[4] = {q.x, q.y, q.z, q.w};
+		u32 cur = wd[0] & 255u, run = 0;                // runs of equal digits (sorted data) fold into one atomic
+		#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const u32 c = (wd[k >> 2] >> ((k & 3) * 8)) & 255u;
+			if (c != cur) { atomicAdd(&hw[cur], run); cur = c; run = 0; }
+			run++;
+		}
+		atomicAdd(&hw[cur], run);
+	} else {
+		for (u32 k = p; k < n && k < p + 16; k++) atomicAdd(&hw[digits[k]], 1u);
+	}
+	__syncthreads();
+	u32 s = 0;
+	#pragma unroll
+	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
+	tile_hist[(size_t)t * stride + blockIdx.x] = s;
+}
+
 // block d: total of digit d over all tiles (one coalesced row)
 __global__ void __launch_bounds__(256) k_rs_totals(const u32* __restrict__ tile_hist, u32 tiles, u32 stride, u32* __restrict__ totals)
 {
@@ -103,7 +135,8 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const K* __restrict__ kin, const u32* __restrict__ vin,
                                                            K* __restrict__ kout, u32* __restrict__ vout,
-                                                           const u32* __restrict__ tile_off, u32 stride, u32 n, int shift)
+                                                           const u32* __restrict__ tile_off, u32 stride, u32 n, int shift,
+                                                           u8* __restrict__ dnext = nullptr, int next_shift = 0)
 {
 	extern __shared__ __align__(16) u8 rs_smem[];
 	K* skey = reinterpret_cast<K*>(rs_smem);
@@ -170,6 +203,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 		const u32 dst = g_off[rs_digit(k, shift)] + j;
 		kout[dst] = k;
 		vout[dst] = sval[j];
+		if (dnext) dnext[dst] = (u8)rs_digit(k, next_shift);   // the next pass counts this byte instead of re-reading the key
 	}
 }
 
@@ -310,6 +344,7 @@ struct RadixBuffers {
 	u64* k[2]; u32* v[2];
 	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries; the look-back words of the one-sweep passes
 	u32* totals;      // 256
+	u8*  dnext;       // n bytes (or null): digit of the next pass, written by the scatter, read by k_rs_hist_bytes
 	u32* os_state;    // one-sweep: digit histograms of every pass [8][256], then the tile ticket
 	int* err;
 	bool classic;     // three-kernel passes (A/B switch, and blocks of 2^30 keys or more)
@@ -347,10 +382,15 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 		return cur;
 	}
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		if (!(first_hist_ready && shift == bit_lo)) { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
+		if (shift == bit_lo) {
+			if (!first_hist_ready) { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
+		} else if (b.dnext) { k_rs_hist_bytes<<<tiles, RS_THREADS, 0, s>>>(b.dnext, n, b.tile_hist, stride); *launches += 1; }
+		else { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
 		k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
 		k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
-		k_rs_scatter<u64><<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift);
+		const bool more = shift + 8 < bit_hi;
+		k_rs_scatter<u64><<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], b.tile_hist, stride, n, shift,
+		                                                              more ? b.dnext : nullptr, shift + 8);
 		*launches += 3;
 		cur ^= 1;
 	}
