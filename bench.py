@@ -11,8 +11,10 @@ The forward transform of the same block (configs[2]/[3] shape) is reported in th
   value     MB/s (1e6 bytes of block per second) with the block resident in HBM, CUDA events around K steps
   e2e       the same through the host C-ABI (jp_bwt_inverse): pinned host block in, pinned host block out,
             both copies inside the timed region
-  roofline  the inverse walk (the two LF-walk kernels + ranking) against the measured HBM copy bandwidth of
-            MEASURED_PEAKS.json, at SURVEY.md 8d's 64 B of random sectors per byte; `rand_peak` is the random
+  roofline  the inverse walk (decode walk + ranking + placement; on blocks under 48 Mi the two LF-walk kernels +
+            ranking) against the measured HBM copy bandwidth of MEASURED_PEAKS.json, at SURVEY.md 8d's 64 B of
+            random sectors per byte -- the figure is fixed by the problem, the single-walk path itself gathers
+            one sector per byte; `rand_peak` is the random
             32 B-sector gather rate measured live by the library's own micro-benchmark
   cpu_baseline  the unmodified reference (oracle/_ref) on this box's host cores, block-parallel like
             Jampack::Compress/Decompress (jampack.cpp:215-219, :313-317): one block per core
@@ -384,14 +386,17 @@ def main():
         walk_ms = (inv_acc[2] + inv_acc[3] + inv_acc[4]) / K                        # both walk kernels + ranking
         algo_bytes = 64.0 * nlen                                                    # 2 random sectors / byte
         achieved = algo_bytes / (walk_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_inv_walk_len + k_inv_rank + k_inv_walk_emit", "achieved": round(achieved, 1),
+        single_walk = inv_stats.get("stream_chunks", 0) > 0       # blocks of 48 Mi and more: every LF entry gathered once
+        walk_kernels = "k_inv_walk_stream + k_inv_rank_packed + k_inv_place" if single_walk else "k_inv_walk_len + k_inv_rank + k_inv_walk_emit"
+        phase_names = ("hist_ctable", "lf_build", "walk_stream", "rank", "place") if single_walk else ("hist_ctable", "lf_build", "walk_len", "rank", "walk_emit")
+        roof = {"bound": "hbm", "kernel": walk_kernels, "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_pair": algo_bytes, "ms_per_step": round(walk_ms, 4),
-                "traffic": ncu_traffic("inverse_walk"),
+                "traffic": ncu_traffic("inverse_walk_single" if single_walk else "inverse_walk"),
                 "rand_peak": round(rand_rate * 32 / 1e9, 1), "rand_unit": "GB/s of 32 B sectors = live dependent-gather micro-benchmark over a table of the LF table's size x 32 B",
                 "rand_gathers_per_s": round(rand_rate / 1e9, 2),
                 "frac_of_rand": round(achieved / (rand_rate * 32 / 1e9), 4),
-                "phases_ms": {k: round(v / K, 4) for k, v in zip(("hist_ctable", "lf_build", "walk_len", "rank", "walk_emit"), inv_acc.values())}}
+                "phases_ms": {k: round(v / K, 4) for k, v in zip(phase_names, inv_acc.values())}}
         line = {"metric": "inv BWT MB/s", "value": round(CALLERS * total_bytes / (inv_c_max * 1e-3) / 1e6, 1), "unit": "MB/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(inv_c_max / K, 4), "blocks_per_step_per_gpu": CALLERS,
                 "single_stream": {"value": round(total_bytes / (inv_ms_max * 1e-3) / 1e6, 1), "ms_per_block": round(inv_ms_max / K, 4),
@@ -406,7 +411,7 @@ def main():
                         "single_caller": {"value": round(total_bytes / (inv_e2e_max * 1e-3) / 1e6, 1), "ms_per_step": round(inv_e2e_max / K, 4),
                                           "h2d_bytes_per_step": n + TRAILER, "d2h_bytes_per_step": n}},
                 "gpu_launches": inv_c_launches, "clocks": clk, "roofline": roof, "parity": parity,
-                "inverse_stats": {k: inv_stats[k] for k in ("subchains", "subchain_spacing", "device_bytes", "kernel_launches")},
+                "inverse_stats": {k: inv_stats[k] for k in ("subchains", "subchain_spacing", "device_bytes", "kernel_launches", "stream_chunks", "random_sectors")},
                 "host_cores": os.cpu_count()}
         if fwd:
             st = fwd[3]

@@ -110,7 +110,10 @@ typedef struct jp_bwt_stats {
 	float    ms_h2d, ms_d2h;     /* host entry points only                                             */
 	float    ms_phase[8];        /* forward: 0 keys 1 initial sort 2 initial ranks 3 rounds 4 emit      */
 	                             /* inverse: 0 prepare+histogram 1 LF build 2 length walk 3 ranking 4 emit walk */
+	                             /*          (single-walk path: 2 decode walk 3 ranking 4 placement + copy)     */
 	float    active_fraction[JP_BWT_MAX_ROUNDS]; /* forward: a_r = suffixes still unsorted entering round r */
+	int32_t  stream_chunks;      /* inverse: 1 KiB stream chunks the single-walk path used; 0 = two-pass path,  */
+	                             /* negative = the stream space overflowed and the two-pass path was rerun      */
 } jp_bwt_stats;
 
 /* Stats of the last call made by the calling thread. */

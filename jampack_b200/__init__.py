@@ -36,7 +36,7 @@ class Stats(C.Structure):
                 ("initial_depth", C.c_int32), ("subchains", C.c_int32), ("subchain_spacing", C.c_int32),
                 ("device_bytes", C.c_uint64), ("random_sectors", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_phase", C.c_float * 8), ("active_fraction", C.c_float * MAX_ROUNDS)]
+                ("ms_phase", C.c_float * 8), ("active_fraction", C.c_float * MAX_ROUNDS), ("stream_chunks", C.c_int32)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_phase", "active_fraction")}
@@ -159,8 +159,14 @@ def inverse(block, out=None):
 
 # ---- device-resident entry points (torch CUDA uint8 tensors) ------------------------------------------
 def _stream_of(t):
+    """The torch stream the caller's tensors are ordered on. The legacy default stream has handle 0, which the C-ABI
+    reads as "use the context's own (non-blocking) stream": pending torch work on it is drained first, or the stage
+    could start before the caller's fill/clone of its blocks has finished."""
     import torch
-    return torch.cuda.current_stream(t.device).cuda_stream
+    st = torch.cuda.current_stream(t.device)
+    if st.cuda_stream == 0:
+        st.synchronize()
+    return st.cuda_stream
 
 
 def forward_device(d_in, d_out=None):

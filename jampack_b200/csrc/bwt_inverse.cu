@@ -498,6 +498,251 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 	}
 }
 
+// ---- single-walk path ----------------------------------------------------------------------------------
+// The two passes above gather every LF entry twice (once for the lengths, once for the bytes): 2 * nlen random
+// sectors. For large blocks the walk is done ONCE: a walker decodes its sub-chain while it measures it and parks
+// the bytes in a per-warp stream (row r of a warp's stream = the 32 bytes its lanes produced in loop iteration r,
+// one coalesced 32 B store). After the ranking has told every sub-chain where it ends, k_inv_place REPLAYS each
+// warp's loop -- same tickets, same lane assignment, no gathers -- reading the rows back in order and writing the
+// bytes to their text positions with the same 16-byte window logic as k_inv_walk_emit.
+//   * The replay is deterministic given (a) the ticket batches the warp drew (logged: batch_head/batch_next) and
+//     (b) each sub-chain's length, which rides in the top bits of its record through the ranking.
+//   * Streams are carved in 1 KiB chunks (32 rows) from a bump counter; chunks live in the OUTPUT block and in the
+//     part of the consumed input block the records leave free, so the call still fits 6N: the placed text is
+//     assembled in the (by then dead) LF table and copied to the output at the end.
+//   * Tail rows (lanes idle while the warp's last sub-chains finish) are the overhead: ~25 % of nlen for 64 MiB.
+//     If the chunk space or a length field overflows, DE_STREAM_OVERFLOW is raised and the host reruns the
+//     two-pass path on the intact LF table.
+constexpr int ST_ROWS  = 32;
+constexpr int ST_CHUNK = ST_ROWS * 32;           // bytes per stream chunk
+constexpr int ST_AHEAD = 8;                      // rows before a chunk fills at which the next one is requested
+constexpr int PR_DIST_BITS = 24, PR_NXT_BITS = 26;
+constexpr u32 PR_DIST_MASK = (1u << PR_DIST_BITS) - 1, PR_NXT_MASK = (1u << PR_NXT_BITS) - 1;
+constexpr u32 PR_NXT_INVALID = PR_NXT_MASK;
+constexpr u32 PR_LEN_MAX = (1u << (64 - PR_DIST_BITS - PR_NXT_BITS)) - 1;
+constexpr u32 ST_NONE = 0xffffffffu;
+
+__device__ __forceinline__ u64 pack3(u32 len, u32 nxt, u32 dist) { return ((u64)len << (PR_DIST_BITS + PR_NXT_BITS)) | ((u64)nxt << PR_DIST_BITS) | dist; }
+__device__ __forceinline__ u32 pr_len(u64 r)  { return (u32)(r >> (PR_DIST_BITS + PR_NXT_BITS)); }
+__device__ __forceinline__ u32 pr_nxt(u64 r)  { return (u32)(r >> PR_DIST_BITS) & PR_NXT_MASK; }
+__device__ __forceinline__ u32 pr_dist(u64 r) { return (u32)r & PR_DIST_MASK; }
+
+struct StreamSpace {
+	u8* base0; u32 cap0;           // chunks [0, cap0) live here (the output block) ...
+	u8* base1; u32 cap1;           // ... chunks [cap0, cap0 + cap1) here (free part of the consumed input, or workspace)
+	u32* chunk_head;               // [walker warp] first chunk of the warp's stream
+	u32* chunk_next;               // [chunk] the chunk that follows in the same stream
+	u32* batch_head;               // [walker warp] first ticket batch the warp drew (batch = base / WALK_BATCH)
+	u32* batch_next;               // [batch] the batch the same warp drew next
+	u32  batch_cap;
+};
+__device__ __forceinline__ u8* chunk_ptr(const StreamSpace& sp, u32 c)
+{
+	return c < sp.cap0 ? sp.base0 + (size_t)c * ST_CHUNK : sp.base1 + (size_t)(c - sp.cap0) * ST_CHUNK;
+}
+
+// take_ticket, with the batch bases logged per warp (prev_batch is lane 0's)
+__device__ __forceinline__ u32 take_ticket_log(WarpTickets& wt, bool need, u32* __restrict__ ticket, u32 nodes, bool& done,
+                                               u32& prev_batch, u32 wgid, const StreamSpace& sp, int* __restrict__ err)
+{
+	const u32 nm = __ballot_sync(0xffffffffu, need);
+	if (nm == 0) return REC_INVALID;
+	const u32 cnt = __popc(nm), r = __popc(nm & lanemask_lt()), avail = wt.end - wt.next;
+	u32 my = REC_INVALID;
+	if (need && r < avail) my = wt.next + r;
+	if (cnt > avail) {
+		u32 base = 0;
+		if (lane_id() == 0) {
+			base = atomicAdd(ticket, WALK_BATCH);
+			const u32 kb = base / WALK_BATCH;
+			if (kb < sp.batch_cap) { if (prev_batch == ST_NONE) sp.batch_head[wgid] = kb; else sp.batch_next[prev_batch] = kb; }
+			else dev_fail(err, DE_STREAM_OVERFLOW);
+			prev_batch = kb;
+		}
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (need && r >= avail) my = base + (r - avail);
+		wt.next = base + (cnt - avail);
+		wt.end = base + WALK_BATCH;
+	} else wt.next += cnt;
+	if (need && my >= nodes) { done = true; my = REC_INVALID; }
+	return my;
+}
+
+__global__ void __launch_bounds__(INV_THREADS) k_inv_walk_stream(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
+                                                                 i32 n, int log2m, u32 S, u64* __restrict__ rec,
+                                                                 u32* __restrict__ ticket, u32* __restrict__ chunk_ctr,
+                                                                 StreamSpace sp, int* __restrict__ err)
+{
+	__shared__ AnchorTable anchors;
+	__shared__ i32 C[257];
+	load_anchor_table(anchors, meta);
+	for (int i = threadIdx.x; i < 257; i += blockDim.x) C[i] = meta->ctable[i];
+	__syncthreads();
+	const i32 idx = meta->idx;
+	const u32 nodes = S + N_ANCHOR;
+	const u32 lane = lane_id();
+	const u32 wgid = blockIdx.x * INV_WARPS + (threadIdx.x >> 5);
+	const u32 cap = sp.cap0 + sp.cap1;
+	const u64 pol_ld = policy_evict_first();
+	WarpTickets wt = {0, 0};
+	u32 id = REC_INVALID, v = 0, len = 0;
+	u32 prev_batch = ST_NONE, chunk = ST_NONE, nextc = 0, row = ST_ROWS;
+	u8* cp = nullptr;
+	bool done = false;
+	for (;;) {
+		const u32 my = take_ticket_log(wt, !done && id == REC_INVALID, ticket, nodes, done, prev_batch, wgid, sp, err);
+		if (my != REC_INVALID) {
+			i32 bi = node_start(my, S, n, log2m, meta, idx);
+			if (bi >= 0 && my < S && is_anchor_row(anchors, bi + (bi >= idx ? 1 : 0))) bi = -1;
+			if (bi < 0) rec[my] = pack3(0, PR_NXT_INVALID, 0);
+			else { id = my; len = 0; v = ld_lf(lf + bi, pol_ld, false); }
+		}
+		if (__ballot_sync(0xffffffffu, !done) == 0) break;
+		if (row == ST_ROWS) {                                   // this iteration opens a new chunk (warp-uniform)
+			if (chunk == ST_NONE && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);
+			const u32 c = __shfl_sync(0xffffffffu, nextc, 0);
+			if (c >= cap) { dev_fail(err, DE_STREAM_OVERFLOW); break; }
+			if (lane == 0) { if (chunk == ST_NONE) sp.chunk_head[wgid] = c; else sp.chunk_next[chunk] = c; }
+			chunk = c; cp = chunk_ptr(sp, c); row = 0;
+		}
+		if (row == ST_ROWS - ST_AHEAD && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);   // consumed ST_AHEAD iterations from now
+		if (id != REC_INVALID) {
+			const i32 r = (i32)(v & LF_MASK);
+			len++;
+			bool stop = (r == idx);
+			u32 nxt = S;
+			if (!stop) {
+				const i32 bi = row_to_byte(r, idx);
+				v = ld_lf(lf + bi, pol_ld, false);               // next gather goes out before the symbol search below
+				if (v & LF_MARK) { stop = true; nxt = node_of(anchors, r, bi, log2m, S); }
+			}
+			cp[row * 32 + lane] = (u8)symbol_of_row(C, r);
+			if (stop) {
+				if (len > PR_LEN_MAX) { dev_fail(err, DE_STREAM_OVERFLOW); len = PR_LEN_MAX; }
+				rec[id] = pack3(len, nxt, len);
+				id = REC_INVALID;
+			}
+		}
+		row++;
+	}
+}
+
+// Pointer jumping over the packed records; the length field of a record is its own and is carried along.
+__global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int hop_cap)
+{
+	const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 nodes = S + N_ANCHOR;
+	if (id >= nodes || *(volatile int*)err != 0) return;
+	volatile u64* vrec = rec;
+	const u64 r = vrec[id];
+	const u32 len = pr_len(r);
+	u32 nxt = pr_nxt(r), dist = pr_dist(r);
+	if (nxt == PR_NXT_INVALID) return;
+	int hops = 0;
+	while (nxt < S) {
+		const u64 o = vrec[nxt];
+		const u32 onxt = pr_nxt(o);
+		dist += pr_dist(o);
+		if (onxt == PR_NXT_INVALID || ++hops > hop_cap) { dev_fail(err, DE_RANK_LOOP); nxt = S; dist = 0; break; }
+		if (dist > PR_DIST_MASK) { dev_fail(err, DE_CHAIN_LEN); nxt = S; dist = 0; break; }   // no honest chain is longer than a unit
+		nxt = onxt;
+		vrec[id] = pack3(len, nxt, dist);
+	}
+	vrec[id] = pack3(len, nxt, dist);
+	if (id > S && (nxt != id - 1 || dist != (u32)step)) dev_fail(err, DE_CHAIN_LEN);
+}
+
+// Zeroes the area the text is assembled in -- the head of the LF table -- unless the walk failed: the two-pass rerun
+// needs the table intact (in consume mode the BWT itself is gone by then).
+__global__ void __launch_bounds__(256) k_inv_clear_text(uint4* __restrict__ text, u32 n16, const int* __restrict__ err)
+{
+	if (*(volatile const int*)err != 0) return;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) text[i] = make_uint4(0, 0, 0, 0);
+}
+
+// Replay of k_inv_walk_stream's loop: iteration i of warp w reads row i of w's stream.
+__global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 S, const u64* __restrict__ rec,
+                                                           StreamSpace sp, u8* __restrict__ out, int* __restrict__ err)
+{
+	__shared__ uint4 sdata[INV_WARPS][ST_CHUNK / 16];
+	__shared__ u64 srec[INV_WARPS][2][WALK_BATCH];
+	if (*(volatile int*)err != 0) return;                       // the stream is incomplete: the host falls back
+	const u32 nodes = S + N_ANCHOR;
+	const u32 lane = lane_id(), w = threadIdx.x >> 5;
+	const u32 wgid = blockIdx.x * INV_WARPS + w;
+	const u32 cap = sp.cap0 + sp.cap1;
+	const u8* sbytes = reinterpret_cast<const u8*>(sdata[w]);
+	u32 next_t = 0, end_t = 0, base_t = 0, par = 0;
+	u32 prev_batch = ST_NONE, chunk = ST_NONE, row = ST_ROWS;
+	u32 id = REC_INVALID, left = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+	i32 pos = 0, pos_end = 0;
+	bool done = false, bad = false;
+	// (a replay that has diverged from the walk -- only possible after a failed check -- must not chase stale log
+	// entries: any failure ends the warp, and the iteration count is bounded by the rows that exist)
+	for (u32 iter = 0; iter < cap * ST_ROWS + 2; iter++) {
+		// ---- the ticket logic of take_ticket_log, batches read back from the log, records from shared memory
+		const bool need = !done && id == REC_INVALID;
+		const u32 nm = __ballot_sync(0xffffffffu, need);
+		if (nm != 0) {
+			const u32 cnt = __popc(nm), r = __popc(nm & lanemask_lt()), avail = end_t - next_t;
+			u32 my = REC_INVALID; u64 rv = 0;
+			if (need && r < avail) { my = next_t + r; rv = srec[w][par][my - base_t]; }
+			if (cnt > avail) {
+				u32 kb = 0;
+				if (lane == 0) { kb = (prev_batch == ST_NONE) ? sp.batch_head[wgid] : sp.batch_next[prev_batch]; prev_batch = kb; }
+				kb = __shfl_sync(0xffffffffu, kb, 0);
+				if (kb >= sp.batch_cap) { dev_fail(err, DE_STREAM_OVERFLOW); break; }
+				const u32 base = kb * WALK_BATCH;
+				par ^= 1;
+				__syncwarp();
+				#pragma unroll
+				for (int k = 0; k < (int)WALK_BATCH / 32; k++) {
+					const u32 q = base + k * 32 + lane;
+					srec[w][par][k * 32 + lane] = q < nodes ? rec[q] : pack3(0, PR_NXT_INVALID, 0);
+				}
+				__syncwarp();
+				if (need && r >= avail) { my = base + (r - avail); rv = srec[w][par][my - base]; }
+				next_t = base + (cnt - avail); end_t = base + WALK_BATCH; base_t = base;
+			} else next_t += cnt;
+			if (need && my >= nodes) { done = true; my = REC_INVALID; }
+			if (my != REC_INVALID && pr_nxt(rv) != PR_NXT_INVALID) {
+				const u32 nxt = pr_nxt(rv), L = pr_len(rv);
+				const i64 pe = (i64)(nxt - S) * step + pr_dist(rv);
+				if (nxt < S || nxt >= nodes || L == 0 || pe > n || pe < (i64)L) { dev_fail(err, DE_CHAIN_RANGE); bad = true; }
+				else { id = my; left = L; pos = pos_end = (i32)pe; a0 = a1 = a2 = a3 = 0; }
+			}
+		}
+		if (__any_sync(0xffffffffu, bad)) break;
+		if (__ballot_sync(0xffffffffu, !done) == 0) break;
+		if (row == ST_ROWS) {
+			u32 c = 0;
+			if (lane == 0) c = (chunk == ST_NONE) ? sp.chunk_head[wgid] : sp.chunk_next[chunk];
+			c = __shfl_sync(0xffffffffu, c, 0);
+			if (c >= cap) { dev_fail(err, DE_STREAM_OVERFLOW); break; }
+			const uint4* src = reinterpret_cast<const uint4*>(chunk_ptr(sp, c));
+			__syncwarp();
+			sdata[w][lane] = __ldcs(src + lane);
+			sdata[w][32 + lane] = __ldcs(src + 32 + lane);
+			__syncwarp();
+			chunk = c; row = 0;
+		}
+		if (id != REC_INVALID) {
+			const u32 c = sbytes[row * 32 + lane];
+			pos--; left--;
+			const bool stop = left == 0;
+			const u32 k = ((u32)pos >> 2) & 3u, bits = c << (((u32)pos & 3u) * 8);
+			a0 |= (k == 0) ? bits : 0u; a1 |= (k == 1) ? bits : 0u; a2 |= (k == 2) ? bits : 0u; a3 |= (k == 3) ? bits : 0u;
+			if (((u32)pos & 15u) == 0 || stop) {
+				const i32 wbase = pos & ~15;
+				flush_window(out + wbase, (u32)(pos - wbase), (u32)min(16, pos_end - wbase), a0, a1, a2, a3);
+				a0 = a1 = a2 = a3 = 0;
+			}
+			if (stop) id = REC_INVALID;
+		}
+		row++;
+	}
+}
+
 // ---- host driver -----------------------------------------------------------------------------------
 // Marker spacing m. A pass costs about nlen / (gather rate) + (longest sub-chain) * (unloaded DRAM latency), and
 // the longest of nlen/m geometric sub-chains is ~ m * ln(nlen/m): measured on 64 MiB, m = 64 / 32 / 16 give
@@ -524,19 +769,69 @@ static int walker_blocks(Ctx& c, const void* kernel)
 struct InvBuffers {
 	u32* lf; u32* tile_hist; u32* bin_total; InvMeta* meta; u64* rec; u32* ticket; int* err;
 	int tiles; int log2m; u32 S;
+	bool single;                  // single-walk path (k_inv_walk_stream / k_inv_place)
+	int  wblocks;                 // walker blocks of the single-walk kernels (the replay needs the same grid)
+	StreamSpace sp;
 };
+
+// Single-walk path: on by default for blocks of 48 Mi and more, where the stream overhead (tail rows, ~76 per
+// walker warp) fits beside the records in the consumed input block. JP_BWT_INV_SINGLE=0 turns it off, =1 forces it
+// for every block of 64 Ki and more with the stream space topped up from the workspace (tests).
+static int single_mode()
+{
+	if (const char* e = getenv("JP_BWT_INV_SINGLE")) return atoi(e) != 0 ? 1 : 0;
+	return -1;
+}
 
 // `scratch_in`: when the caller's input block may be overwritten once the LF table is built, the sub-chain
 // records live there (8 * nodes <= nlen bytes) and the workspace is lf + per-tile histograms: 6N + N/64 in all.
-static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr)
+static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, u8* d_out = nullptr)
 {
 	b.tiles = (int)(((i64)nlen + INV_TILE - 1) / INV_TILE);
 	b.log2m = pick_log2m(nlen);
 	b.S = (u32)(((i64)nlen + (1 << b.log2m) - 1) >> b.log2m);
 	const size_t nodes = (size_t)b.S + N_ANCHOR;
 	const bool rec_in_input = scratch_in != nullptr && nodes * 8 <= (size_t)nlen && ((uintptr_t)scratch_in & 7) == 0;
+
+	// stream space of the single-walk path
+	const int mode = single_mode();
+	b.single = d_out != nullptr && ((uintptr_t)d_out & 15) == 0 && nodes < PR_NXT_INVALID && (u32)(nlen / JP_BWT_UNITS) <= PR_DIST_MASK &&
+	           (mode == 1 ? nlen >= (1 << 16) : (mode == -1 && nlen >= (48 << 20)));
+	size_t extra_stream = 0, in_free_off = 0, in_free = 0;
+	b.wblocks = 0;
+	b.sp = StreamSpace{};
+	if (b.single) {
+		// every lane should see a handful of sub-chains, or the tail rows dominate the stream
+		// (measured on 64 MiB: 8 / 6 / 5 / 4 / 3 blocks per SM walk in 1.154 / 1.142 / 1.146 / 1.173 / 1.388 ms and leave
+		// streams of 1.32 / 1.24 / 1.20 / 1.16 / 1.12 nlen: the gathers saturate DRAM from 4 blocks per SM on, and every
+		// walker warp adds ~76 tail rows)
+		int resident = walker_blocks(c, (const void*)k_inv_walk_stream), per_sm = 5;
+		if (const char* e = getenv("JP_BWT_INV_WBLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
+		resident = std::min(resident, per_sm * c.sm_count);
+		b.wblocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)resident, nodes / (INV_THREADS * 8)));
+		if (rec_in_input) {
+			in_free_off = (nodes * 8 + 15) & ~(size_t)15;
+			in_free = (size_t)nlen > in_free_off ? (size_t)nlen - in_free_off : 0;
+		} else extra_stream = (size_t)nlen / 2;
+		if (mode == 1) extra_stream += (size_t)nlen / 2 + (size_t)b.wblocks * INV_WARPS * 160 * 32;
+		b.sp.cap0 = (u32)((size_t)nlen / ST_CHUNK);
+		b.sp.batch_cap = (u32)(nodes / WALK_BATCH + (size_t)b.wblocks * INV_WARPS * 4 + 16);
+	}
+	const size_t walker_warps = (size_t)b.wblocks * INV_WARPS;
+	if (const char* e = getenv("JP_BWT_INV_STREAM_CAP")) {          // tests: shrink the stream space to provoke the two-pass rerun
+		const long v = atol(e);
+		if (b.single && v >= 0 && (u32)v < b.sp.cap0) { b.sp.cap0 = (u32)v; in_free = 0; extra_stream = 0; }
+	}
+	const u32 cap_in = (u32)(in_free / ST_CHUNK), cap_extra = (u32)(extra_stream / ST_CHUNK);
+	if (b.single) {
+		// region 1 is ONE address range: the free part of the input when there is no top-up, else the workspace piece
+		// alone (the input's free part is then left unused -- only tests and the non-consuming entry point get here)
+		b.sp.cap1 = cap_extra > 0 ? cap_extra : cap_in;
+	}
 	size_t total = Arena::align((size_t)nlen * 4) + Arena::align((size_t)b.tiles * 256 * 4) + Arena::align(256 * 4) +
 	               Arena::align(sizeof(InvMeta)) + (rec_in_input ? 0 : Arena::align(nodes * 8)) + Arena::align(64) + Arena::align(64);
+	if (b.single) total += Arena::align((size_t)cap_extra * ST_CHUNK) + 2 * Arena::align(walker_warps * 4) +
+	                       Arena::align(((size_t)b.sp.cap0 + b.sp.cap1) * 4) + Arena::align((size_t)b.sp.batch_cap * 4);
 	JP_TRY(arena_reserve(c, total));
 	b.lf = arena_take<u32>(c, (size_t)nlen);
 	b.tile_hist = arena_take<u32>(c, (size_t)b.tiles * 256);
@@ -545,6 +840,14 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr)
 	b.rec = rec_in_input ? reinterpret_cast<u64*>(scratch_in) : arena_take<u64>(c, nodes);
 	b.ticket = arena_take<u32>(c, 16);
 	b.err = arena_take<int>(c, 16);
+	if (b.single) {
+		b.sp.base0 = d_out;
+		b.sp.base1 = cap_extra > 0 ? arena_take<u8>(c, (size_t)cap_extra * ST_CHUNK) : scratch_in + in_free_off;
+		b.sp.chunk_head = arena_take<u32>(c, walker_warps);
+		b.sp.batch_head = arena_take<u32>(c, walker_warps);
+		b.sp.chunk_next = arena_take<u32>(c, (size_t)b.sp.cap0 + b.sp.cap1);
+		b.sp.batch_next = arena_take<u32>(c, b.sp.batch_cap);
+	}
 	return JP_OK;
 }
 
@@ -576,7 +879,7 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	}
 	const i32 step = nlen / JP_BWT_UNITS;                               // bwt.cpp:176 with N_Units = 120
 	InvBuffers b;
-	JP_TRY(inv_alloc(c, nlen, b, scratch_in));
+	JP_TRY(inv_alloc(c, nlen, b, scratch_in, d_out));
 	JP_TRY(inv_build_table(c, d_in, len, nlen, d_out, b, s));
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
@@ -584,31 +887,61 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
 	const u32 nodes = b.S + N_ANCHOR;
-	const int wb1 = walker_blocks(c, (const void*)k_inv_walk_len);
-	k_inv_walk_len<<<wb1, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, walk_flags()); JP_LAUNCH(c);
-	JP_KCHECK();
-	JP_CUDA(cudaEventRecord(c.ev[3], s));
-	// (a two-level scheme -- majors walk to majors, jump, hand down -- was tried: 0.86 ms against 0.28 ms; the
-	// dependent record-to-record walks are latency-bound, the flat jumping is not)
 	// a decode unit holds about nodes/120 sub-chains, so no honest list is longer than a few times that; the cap
 	// only bounds the time spent on a corrupt block whose records form cycles
 	const int hop_cap = (int)std::min<u64>((u64)RANK_HOP_CAP, (u64)nodes / 16 + 4096);
-	k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, 1, hop_cap); JP_LAUNCH(c);
-	JP_KCHECK();
-	JP_CUDA(cudaEventRecord(c.ev[4], s));
-	JP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nlen, s));               // shared words of neighbouring sub-chains are merged by RED.OR
-	const int wb2 = walker_blocks(c, (const void*)k_inv_walk_emit);
-	k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err, walk_flags()); JP_LAUNCH(c);
-	JP_KCHECK();
-	JP_CUDA(cudaEventRecord(c.ev[5], s));
-	JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
-	JP_CUDA(cudaStreamSynchronize(s));
+	st->stream_chunks = 0;
+	bool two_pass = !b.single;
+	if (b.single) {
+		u8* text = reinterpret_cast<u8*>(b.lf);                             // the LF table is dead once the walk is over
+		k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[3], s));
+		k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[4], s));
+		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);
+		k_inv_place<<<b.wblocks, INV_THREADS, 0, s>>>(nlen, step, b.S, b.rec, b.sp, text, b.err); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaMemcpyAsync(d_out, text, (size_t)nlen, cudaMemcpyDeviceToDevice, s));   // (meaningless but harmless after a failure)
+		JP_CUDA(cudaEventRecord(c.ev[5], s));
+		JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+		JP_CUDA(cudaMemcpyAsync(c.h_small + 4, b.ticket + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		st->stream_chunks = (i32)std::min<u32>((u32)c.h_small[4], 0x7fffffffu);
+		st->random_sectors = (u64)nlen;
+		if (c.h_small[0] == DE_STREAM_OVERFLOW) {                           // rare: rerun on the intact LF table
+			two_pass = true;
+			st->stream_chunks = -st->stream_chunks;
+			JP_CUDA(cudaMemsetAsync(b.ticket, 0, 64, s));
+			JP_CUDA(cudaMemsetAsync(b.err, 0, 64, s));
+			JP_CUDA(cudaEventRecord(c.ev[2], s));
+		}
+	}
+	if (two_pass) {
+		const int wb1 = walker_blocks(c, (const void*)k_inv_walk_len);
+		k_inv_walk_len<<<wb1, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, walk_flags()); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[3], s));
+		// (a two-level scheme -- majors walk to majors, jump, hand down -- was tried: 0.86 ms against 0.28 ms; the
+		// dependent record-to-record walks are latency-bound, the flat jumping is not)
+		k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, 1, hop_cap); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[4], s));
+		JP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nlen, s));               // shared words of neighbouring sub-chains are merged by RED.OR
+		const int wb2 = walker_blocks(c, (const void*)k_inv_walk_emit);
+		k_inv_walk_emit<<<wb2, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, step, b.log2m, b.S, b.rec, b.ticket + 1, d_out, b.err, walk_flags()); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[5], s));
+		JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		st->random_sectors = 2ull * (u64)nlen;
+	}
 	for (int i = 0; i < 5; i++) JP_CUDA(cudaEventElapsedTime(&st->ms_phase[i], c.ev[i], c.ev[i + 1]));
 	JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[5]));
 	st->subchains = (i32)nodes;
 	st->subchain_spacing = 1 << b.log2m;
 	st->device_bytes = c.arena.high;
-	st->random_sectors = 2ull * (u64)nlen;
 	return map_dev_err(c.h_small[0]);
 }
 

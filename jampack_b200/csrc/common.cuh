@@ -24,6 +24,7 @@ enum DevErr : int {
 	DE_RANK_LOOP = 4,      // inverse: list ranking did not reach an anchor (cyclic garbage input)
 	DE_FWD_RANGE = 5,      // forward: an active suffix asked for a rank beyond the end (invariant)
 	DE_FWD_ROUNDS = 6,     // forward: doubling did not converge within the round limit
+	DE_STREAM_OVERFLOW = 7, // inverse, single-walk path: stream space or a length field ran out (host reruns the two-pass path)
 };
 
 __device__ __forceinline__ void dev_fail(int* flag, int code) { atomicCAS(flag, 0, code); }

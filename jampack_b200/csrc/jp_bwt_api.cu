@@ -35,6 +35,7 @@ int map_dev_err(int de)
 	case DE_RANK_LOOP: set_error_detail("sub-chain ranking found a cycle"); return JP_ERR_CORRUPT;
 	case DE_FWD_RANGE: set_error_detail("forward: rank lookup beyond the end of the block"); return JP_ERR_INTERNAL;
 	case DE_FWD_ROUNDS: set_error_detail("forward: prefix doubling did not converge"); return JP_ERR_INTERNAL;
+	case DE_STREAM_OVERFLOW: set_error_detail("inverse: stream overflow escaped the two-pass rerun"); return JP_ERR_INTERNAL;
 	default: set_error_detail("device error flag %d", de); return JP_ERR_INTERNAL;
 	}
 }

@@ -111,6 +111,8 @@ def test_golden_full_size_blocks(jp, orc, golden):
         assert (back == T).all(), c["name"]
         # inverse stays within 6N + o(N): in (N+480) + out (N) are the caller's, the workspace is lf (4N) + side tables
         assert si.device_bytes <= 4 * c["nlen"] + c["nlen"] // 4 + (1 << 20), (c["name"], si.device_bytes)
+        # blocks this large decode in one walk (every LF entry gathered once); the stream stays inside in + out
+        assert si.stream_chunks > 0 and si.stream_chunks * 1024 <= c["nlen"] + c["nlen"] // 2, (c["name"], si.stream_chunks)
         assert st.rounds <= 40
 
 
@@ -454,3 +456,84 @@ def test_corrupted_bwt_bytes_never_hang_or_crash(jp, orc):
     assert time.time() - t0 < 60
     assert outcomes["error"] > 0
     assert (jp.inverse(B) == T).all()
+
+
+@pytest.fixture
+def single_walk_env():
+    """JP_BWT_INV_* are read per call; restore them whatever the test does."""
+    keys = ("JP_BWT_INV_SINGLE", "JP_BWT_INV_STREAM_CAP", "JP_BWT_INV_WBLOCKS_PER_SM")
+    saved = {k: os.environ.get(k) for k in keys}
+    yield os.environ
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("kind,n,seed", [("markov2", 65536 + 120, 3), ("uniform", MiB, 2), ("repetitive", 2 * MiB + 5, 3),
+                                         ("alla", MiB + 120, 0), ("markov2", 5 * MiB + 77, 4), ("kat_quadratic", 300000, 0)])
+def test_single_walk_inverse_matches_two_pass(jp, orc, single_walk_env, kind, n, seed):
+    """The single-walk inverse (decode once into per-warp streams, rank, replay) is the default from 48 Mi up; forced
+    on here for small blocks. Same bytes as the two-pass path and as the text, through every entry point."""
+    import torch
+    T = orc.gen(kind, n, seed)
+    B = orc.forward(T, _impl(orc))
+    single_walk_env["JP_BWT_INV_SINGLE"] = "0"
+    two_pass = jp.inverse(B)
+    assert jp.last_stats().stream_chunks == 0
+    single_walk_env["JP_BWT_INV_SINGLE"] = "1"
+    one = jp.inverse(B)
+    st = jp.last_stats()
+    assert st.stream_chunks > 0, "single-walk path did not run"
+    assert (one == T).all() and (two_pass == T).all()
+    d_in = torch.from_numpy(B.copy()).cuda()
+    for consume in (False, True):
+        out = jp.inverse_device(d_in.clone(), consume=consume)
+        assert jp.last_stats().stream_chunks > 0
+        assert (out.cpu().numpy()[:n] == T).all()
+    assert (d_in.cpu().numpy() == B).all()                  # the non-consuming entry point left its input alone
+
+
+def test_single_walk_overflow_reruns_two_pass(jp, orc, single_walk_env):
+    """When the stream space runs out the call reruns the two-pass path on the intact LF table: still bit-exact,
+    reported as a negative chunk count."""
+    T = orc.gen("markov2", 3 * MiB, 17)
+    B = orc.forward(T, _impl(orc))
+    single_walk_env["JP_BWT_INV_SINGLE"] = "1"
+    single_walk_env["JP_BWT_INV_STREAM_CAP"] = "100"
+    out = jp.inverse(B)
+    assert jp.last_stats().stream_chunks < 0
+    assert (out == T).all()
+    single_walk_env["JP_BWT_INV_STREAM_CAP"] = "0"
+    assert (jp.inverse(B) == T).all() and jp.last_stats().stream_chunks < 0
+
+
+def test_single_walk_rejects_corrupt_input(jp, orc, single_walk_env):
+    """Same error behaviour as the two-pass path: bad indices -5, inconsistent chains -6, never a hang."""
+    import time
+    single_walk_env["JP_BWT_INV_SINGLE"] = "1"
+    rng = np.random.default_rng(5)
+    T = orc.gen("markov2", MiB, 21)
+    n = T.size
+    B = orc.forward(T, _impl(orc))
+    bad = B.copy()
+    bad[n + 4 * 50: n + 4 * 50 + 4] = np.frombuffer(np.int32(12345).tobytes(), dtype=np.uint8)
+    with pytest.raises(jp.BwtError) as e:
+        jp.inverse(bad)
+    assert e.value.rc == -6
+    t0 = time.time()
+    errors = 0
+    for trial in range(16):
+        bad = B.copy()
+        pos = rng.integers(0, n - n % 120, int(rng.integers(1, 40)))
+        bad[pos] = rng.integers(0, 256, pos.size).astype(np.uint8)
+        if trial % 4 == 3:
+            bad[: n // 2] = bad[n // 2: n // 2 * 2]
+        try:
+            assert jp.inverse(bad).size == n
+        except jp.BwtError as e2:
+            assert e2.rc in (-5, -6), e2
+            errors += 1
+    assert time.time() - t0 < 60 and errors > 0
+    assert (jp.inverse(B) == T).all() and jp.last_stats().stream_chunks > 0
