@@ -894,6 +894,9 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	bool two_pass = !b.single;
 	if (b.single) {
 		u8* text = reinterpret_cast<u8*>(b.lf);                             // the LF table is dead once the walk is over
+		// (serialising the walks of the blocks in flight on one GPU behind a host-side gate, so that the other blocks'
+		// table builds, rankings and placements could fill in beside a single DRAM-bound walk, was measured: 35.3-35.6
+		// against 35.7-36.0 GB/s with four blocks in flight -- the hardware's own interleaving is as good)
 		k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err); JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));

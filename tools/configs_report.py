@@ -29,6 +29,10 @@ for kind, mib, seed in CASES:
         jp.inverse_device(d_B, d_back); i = jp.last_stats().asdict()
         if rep and (best_f is None or f["ms_total"] < best_f["ms_total"]): best_f = f
         if rep and (best_i is None or i["ms_total"] < best_i["ms_total"]): best_i = i
+    d_tmp = d_B.clone()
+    d_back2 = jp.inverse_device(d_tmp, consume=True); ic = jp.last_stats().asdict()   # the 6N variant: the input block is scratch
+    consume_ok = bool(torch.equal(d_back2[:n], d_T))
+    del d_tmp, d_back2
     B = d_B.cpu().numpy()
     key = (kind, n, seed)
     rows.append({"input": f"{kind}({mib} MiB, seed {seed})", "bytes": n,
@@ -38,7 +42,9 @@ for kind, mib, seed in CASES:
                  "forward_workspace_per_byte": round(best_f["device_bytes"] / n, 2), "forward_phases_ms": best_f["ms_phase"][:5],
                  "inverse_ms": round(best_i["ms_total"], 3), "inverse_MBps": round(n / best_i["ms_total"] / 1e3, 1),
                  "inverse_workspace_per_byte": round(best_i["device_bytes"] / n, 3), "inverse_phases_ms": best_i["ms_phase"][:5],
-                 "round_trip": bool(torch.equal(d_back, d_T)),
+                 "inverse_workspace_per_byte_consumed_input": round(ic["device_bytes"] / n, 3),
+                 "inverse_stream_bytes_per_byte": round(abs(best_i["stream_chunks"]) * 1024 / n, 3),
+                 "round_trip": bool(torch.equal(d_back, d_T)) and consume_ok,
                  "forward_matches_reference_hash": (("%016x" % synth.fnv(B)) == gold[key]) if key in gold else None})
     del d_T, d_B, d_back
     torch.cuda.empty_cache()
