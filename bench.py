@@ -11,7 +11,7 @@ The forward transform of the same block (configs[2]/[3] shape) is reported in th
   value     MB/s (1e6 bytes of block per second) with the block resident in HBM, CUDA events around K steps
   e2e       the same through the host C-ABI (jp_bwt_inverse): pinned host block in, pinned host block out,
             both copies inside the timed region
-  roofline  the inverse walk (decode walk + ranking + placement; on blocks under 48 Mi the two LF-walk kernels +
+  roofline  the inverse walk (decode walk + ranking + placement; on blocks under 30 Mi the two LF-walk kernels +
             ranking) against the measured HBM copy bandwidth of MEASURED_PEAKS.json, at SURVEY.md 8d's 64 B of
             random sectors per byte -- the figure is fixed by the problem, the single-walk path itself gathers
             one sector per byte; `rand_peak` is the random
@@ -386,7 +386,7 @@ def main():
         walk_ms = (inv_acc[2] + inv_acc[3] + inv_acc[4]) / K                        # both walk kernels + ranking
         algo_bytes = 64.0 * nlen                                                    # 2 random sectors / byte
         achieved = algo_bytes / (walk_ms * 1e-3) / 1e9
-        single_walk = inv_stats.get("stream_chunks", 0) > 0       # blocks of 48 Mi and more: every LF entry gathered once
+        single_walk = inv_stats.get("stream_chunks", 0) > 0       # blocks of 30 Mi and more: every LF entry gathered once
         walk_kernels = "k_inv_walk_stream + k_inv_rank_packed + k_inv_place" if single_walk else "k_inv_walk_len + k_inv_rank + k_inv_walk_emit"
         phase_names = ("hist_ctable", "lf_build", "walk_stream", "rank", "place") if single_walk else ("hist_ctable", "lf_build", "walk_len", "rank", "walk_emit")
         roof = {"bound": "hbm", "kernel": walk_kernels, "achieved": round(achieved, 1),

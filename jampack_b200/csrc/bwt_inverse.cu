@@ -774,9 +774,10 @@ struct InvBuffers {
 	StreamSpace sp;
 };
 
-// Single-walk path: on by default for blocks of 48 Mi and more, where the stream overhead (tail rows, ~76 per
+// Single-walk path: on by default for blocks of 30 Mi and more, where the stream overhead (tail rows, ~76 per
 // walker warp) fits beside the records in the consumed input block. JP_BWT_INV_SINGLE=0 turns it off, =1 forces it
 // for every block of 64 Ki and more with the stream space topped up from the workspace (tests).
+constexpr i32 SINGLE_WALK_MIN = 30 << 20;   // (a 32 MiB block has nlen = 2^25 - 32)
 static int single_mode()
 {
 	if (const char* e = getenv("JP_BWT_INV_SINGLE")) return atoi(e) != 0 ? 1 : 0;
@@ -796,7 +797,7 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 	// stream space of the single-walk path
 	const int mode = single_mode();
 	b.single = d_out != nullptr && ((uintptr_t)d_out & 15) == 0 && nodes < PR_NXT_INVALID && (u32)(nlen / JP_BWT_UNITS) <= PR_DIST_MASK &&
-	           (mode == 1 ? nlen >= (1 << 16) : (mode == -1 && nlen >= (48 << 20)));
+	           (mode == 1 ? nlen >= (1 << 16) : (mode == -1 && nlen >= SINGLE_WALK_MIN));
 	size_t extra_stream = 0, in_free_off = 0, in_free = 0;
 	b.wblocks = 0;
 	b.sp = StreamSpace{};
@@ -805,7 +806,8 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 		// (measured on 64 MiB: 8 / 6 / 5 / 4 / 3 blocks per SM walk in 1.154 / 1.142 / 1.146 / 1.173 / 1.388 ms and leave
 		// streams of 1.32 / 1.24 / 1.20 / 1.16 / 1.12 nlen: the gathers saturate DRAM from 4 blocks per SM on, and every
 		// walker warp adds ~76 tail rows)
-		int resident = walker_blocks(c, (const void*)k_inv_walk_stream), per_sm = 5;
+		// Under 47 Mi one block per SM less: ~2.5 MB less of tail rows, which is what still fits beside the records.
+		int resident = walker_blocks(c, (const void*)k_inv_walk_stream), per_sm = nlen >= (47 << 20) ? 5 : 4;
 		if (const char* e = getenv("JP_BWT_INV_WBLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
 		resident = std::min(resident, per_sm * c.sm_count);
 		b.wblocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)resident, nodes / (INV_THREADS * 8)));

@@ -474,7 +474,7 @@ def single_walk_env():
 @pytest.mark.parametrize("kind,n,seed", [("markov2", 65536 + 120, 3), ("uniform", MiB, 2), ("repetitive", 2 * MiB + 5, 3),
                                          ("alla", MiB + 120, 0), ("markov2", 5 * MiB + 77, 4), ("kat_quadratic", 300000, 0)])
 def test_single_walk_inverse_matches_two_pass(jp, orc, single_walk_env, kind, n, seed):
-    """The single-walk inverse (decode once into per-warp streams, rank, replay) is the default from 48 Mi up; forced
+    """The single-walk inverse (decode once into per-warp streams, rank, replay) is the default from 30 Mi up; forced
     on here for small blocks. Same bytes as the two-pass path and as the text, through every entry point."""
     import torch
     T = orc.gen(kind, n, seed)
