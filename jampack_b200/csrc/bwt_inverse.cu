@@ -32,8 +32,10 @@ constexpr int  INV_THREADS    = 256;
 constexpr int  INV_WARPS      = INV_THREADS / 32;
 constexpr int  INV_TILE       = 65536;          // bytes per histogram / LF tile
 constexpr int  INV_CHUNK      = INV_WARPS * 512; // bytes ranked per block iteration of the LF build
-constexpr u32  LF_MARK        = 0x80000000u;
-constexpr u32  LF_MASK        = 0x7fffffffu;
+constexpr u32  LF_MARK        = 0x80000000u;     // row starts a sub-chain
+constexpr u32  LF_ANCHOR      = 0x40000000u;     // ... and is one of the 121 anchor rows (set together with LF_MARK)
+constexpr u32  LF_MASK        = 0x3fffffffu;     // row numbers need 30 bits: nlen <= 1000 * 2^20 < 2^30 (format.hpp:22)
+static_assert((u64)JP_BWT_MAX_LEN + 1 <= (u64)LF_MASK, "row numbers must leave bits 30 and 31 free");
 constexpr int  N_ANCHOR       = JP_BWT_UNITS + 1; // anchor k = row of text position k*step, k = 0..120
 constexpr u32  REC_INVALID    = 0xffffffffu;
 constexpr int  RANK_HOP_CAP   = 1 << 22;
@@ -45,6 +47,11 @@ struct InvMeta {
 	i32 sorted_id[N_ANCHOR];       // ... and which anchor each one is
 	i32 ctable[257];               // C[c] = #{bytes < c}; C[256] = nlen
 };
+
+// The marked row of window w (rows [w << log2m, (w + 1) << log2m)): the top log2m bits of a multiplicative hash. It
+// only has to be unrelated to the structure of the text; two instructions, evaluated once per byte by the LF build
+// and once per sub-chain by the walkers (log2m >= 2).
+__device__ __forceinline__ u32 mark_slot(u32 window, int log2m) { return (window * 0x9E3779B1u) >> (32 - log2m); }
 
 // ---- prepare: read + validate the 120 stored indices, sort the anchors, copy the raw tail ---------
 // bwt.cpp:80-89. The trailer sits at byte offset Len, unaligned, native-endian (little on every CUDA host).
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(INV_THREADS, 3) k_inv_lf(const u8* __restrict_
 				const u32 c = (src >> (8 * (lane & 3))) & 255u;
 				u32 v = mycnt[c] + lrank[it];
 				const u32 gi = (u32)gp;
-				if ((gi & mmask) == (mix32(gi >> log2m) & mmask)) v |= LF_MARK;
+				if ((gi & mmask) == mark_slot(gi >> log2m, log2m)) v |= LF_MARK;
 				lf[gp] = v;
 			}
 		}
@@ -234,56 +241,37 @@ __global__ void k_inv_mark_anchors(const InvMeta* __restrict__ meta, u32* __rest
 		i32 i = row_to_byte(meta->anchor_row[k], idx);
 		if (i < 0) i = 0;
 		if (i >= n) i = n - 1;          // only reachable with indices already flagged as bad
-		atomicOr(&lf[i], LF_MARK);
+		atomicOr(&lf[i], LF_MARK | LF_ANCHOR);
 	}
 }
 
 // ---- walkers ---------------------------------------------------------------------------------------
 struct AnchorTable {
-	i32 row[N_ANCHOR];
-	i32 id[N_ANCHOR];
-	u32 bits[32];                  // 1024-bit filter over the anchor rows: almost every marked row is NOT an anchor
+	i32 row[N_ANCHOR];             // anchor rows ascending ...
+	i32 id[N_ANCHOR];              // ... and which anchor each one is
 };
-__device__ __forceinline__ u32 anchor_hash(i32 row) { return mix32((u32)row) & 1023u; }
 
 __device__ __forceinline__ void load_anchor_table(AnchorTable& a, const InvMeta* meta)
 {
-	if (threadIdx.x < 32) a.bits[threadIdx.x] = 0;
-	__syncthreads();
-	for (int i = threadIdx.x; i < N_ANCHOR; i += blockDim.x) {
-		const i32 r = meta->sorted_row[i];
-		a.row[i] = r; a.id[i] = meta->sorted_id[i];
-		const u32 hsh = anchor_hash(r);
-		atomicOr(&a.bits[hsh >> 5], 1u << (hsh & 31));
-	}
+	for (int i = threadIdx.x; i < N_ANCHOR; i += blockDim.x) { a.row[i] = meta->sorted_row[i]; a.id[i] = meta->sorted_id[i]; }
 }
 
-// node id of the marked row `row` (byte index bi): an anchor if it is one, else the window's splitter
-__device__ __forceinline__ u32 node_of(const AnchorTable& a, i32 row, i32 bi, int log2m, u32 S)
+// node id of the marked row `row` (byte index bi) whose LF entry is v: an anchor when the entry says so (121 rows in
+// the whole block: the search below is off the common path), else the window's own node
+__device__ __forceinline__ u32 node_of(const AnchorTable& a, u32 v, i32 row, i32 bi, int log2m, u32 S)
 {
-	const u32 hsh = anchor_hash(row);
-	if (((a.bits[hsh >> 5] >> (hsh & 31)) & 1u) == 0) return (u32)bi >> log2m;
+	if ((v & LF_ANCHOR) == 0) return (u32)bi >> log2m;
 	int lo = 0, hi = N_ANCHOR;          // first position with a.row[pos] >= row
 	while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.row[mid] < row) lo = mid + 1; else hi = mid; }
 	if (lo < N_ANCHOR && a.row[lo] == row) return S + (u32)a.id[lo];
 	return (u32)bi >> log2m;
 }
 
-__device__ __forceinline__ bool is_anchor_row(const AnchorTable& a, i32 row)
-{
-	const u32 hsh = anchor_hash(row);
-	if (((a.bits[hsh >> 5] >> (hsh & 31)) & 1u) == 0) return false;
-	int lo = 0, hi = N_ANCHOR;
-	while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.row[mid] < row) lo = mid + 1; else hi = mid; }
-	return lo < N_ANCHOR && a.row[lo] == row;
-}
-
 // start row (as a byte index) of node `id`, or -1 when the node does not exist
 __device__ __forceinline__ i32 node_start(u32 id, u32 S, i32 n, int log2m, const InvMeta* meta, i32 idx)
 {
 	if (id < S) {
-		const u32 m1 = (1u << log2m) - 1;
-		const u32 bi = (id << log2m) + (mix32(id) & m1);
+		const u32 bi = (id << log2m) + mark_slot(id, log2m);
 		return bi < (u32)n ? (i32)bi : -1;
 	}
 	const u32 k = id - S;
@@ -368,11 +356,15 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restr
 	for (;;) {
 		const u32 my = take_ticket(wt, !done && id == REC_INVALID, ticket, nodes, done);
 		if (my != REC_INVALID) {
-			i32 bi = node_start(my, S, n, log2m, meta, idx);
-			// a window's own mark that happens to sit on an anchor row would duplicate the anchor's sub-chain: drop it
-			if (bi >= 0 && my < S && is_anchor_row(anchors, bi + (bi >= idx ? 1 : 0))) bi = -1;
-			if (bi < 0) rec[my] = pack_rec(REC_INVALID, 0);
-			else { id = my; len = 0; v = ld_lf(lf + bi, pol_ld, lh); }
+			const i32 bi = node_start(my, S, n, log2m, meta, idx);
+			bool live = bi >= 0;
+			if (live) {
+				v = ld_lf(lf + bi, pol_ld, lh);
+				// a window's own mark that happens to sit on an anchor row would duplicate the anchor's sub-chain: drop it
+				live = my >= S || (v & LF_ANCHOR) == 0;
+			}
+			if (!live) rec[my] = pack_rec(REC_INVALID, 0);
+			else { id = my; len = 0; }
 		}
 		if (__ballot_sync(0xffffffffu, !done) == 0) break;
 		if (id != REC_INVALID) {
@@ -382,7 +374,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restr
 			else {
 				const i32 bi = row_to_byte(r, idx);
 				v = ld_lf(lf + bi, pol_ld, lh);
-				if (v & LF_MARK) { rec[id] = pack_rec(node_of(anchors, r, bi, log2m, S), len); id = REC_INVALID; }
+				if (v & LF_MARK) { rec[id] = pack_rec(node_of(anchors, v, r, bi, log2m, S), len); id = REC_INVALID; }
 			}
 		}
 	}
@@ -415,13 +407,32 @@ __global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, 
 	}
 }
 
-__device__ __forceinline__ u32 symbol_of_row(const i32* __restrict__ C, i32 row)
+// F-column symbol of a row: F[row] = c  <=>  C[c] <= row-1 < C[c+1]. A 1024-cell table over the top bits of row-1
+// gives the last symbol starting at or before the cell; a short scan finishes the job (a cell holds parts of two
+// symbols at most unless the symbols in it are rare, and rare symbols are rarely looked up): ~10 instructions against
+// 32 for the 8-level binary search this replaces.
+constexpr int SYM_CELLS = 1024;
+struct SymTable { i32 C[257]; u8 cell[SYM_CELLS]; };
+__device__ __forceinline__ int sym_shift(i32 n) { int sh = 0; while (((u32)n >> sh) >= (u32)SYM_CELLS) sh++; return sh; }
+__device__ __forceinline__ void load_sym_table(SymTable& t, const InvMeta* __restrict__ meta, int sh)   // whole block; ends with a barrier
 {
-	const i32 x = row - 1;              // F[row] = c  <=>  C[c] <= row-1 < C[c+1]
-	u32 lo = 0;
-	#pragma unroll
-	for (u32 s = 128; s > 0; s >>= 1) if (C[lo + s] <= x) lo += s;
-	return lo;
+	for (int i = threadIdx.x; i < 257; i += blockDim.x) t.C[i] = meta->ctable[i];
+	__syncthreads();
+	for (int k = threadIdx.x; k < SYM_CELLS; k += blockDim.x) {
+		const i32 x = (i32)((u32)k << sh);
+		u32 lo = 0;
+		#pragma unroll
+		for (u32 st = 128; st > 0; st >>= 1) if (t.C[lo + st] <= x) lo += st;
+		t.cell[k] = (u8)lo;
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ u32 symbol_of_row(const SymTable& t, int sh, i32 row)
+{
+	const i32 x = row - 1;
+	u32 c = t.cell[(u32)x >> sh];
+	while (t.C[c + 1] <= x) c++;        // C[256] = nlen > x: stops at 255 at the latest
+	return c;
 }
 
 // One aligned 16-byte window of the output, bytes [lo, hi) valid in (a0..a3), the rest zero. Whole words go
@@ -450,9 +461,9 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
                                                                u32* __restrict__ ticket, u8* __restrict__ out,
                                                                int* __restrict__ err, int flags)
 {
-	__shared__ i32 C[257];
-	for (int i = threadIdx.x; i < 257; i += blockDim.x) C[i] = meta->ctable[i];
-	__syncthreads();
+	__shared__ SymTable sym;
+	const int sh = sym_shift(n);
+	load_sym_table(sym, meta, sh);
 	const i32 idx = meta->idx;
 	const u32 nodes = S + N_ANCHOR;
 	const bool lh = (flags & WF_LOAD_EVICT_FIRST) != 0;
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 				v = ld_lf(lf + row_to_byte(r, idx), pol_ld, lh);   // next gather goes out before the symbol search below
 				stop = (v & LF_MARK) != 0;
 			}
-			const u32 c = symbol_of_row(C, r);
+			const u32 c = symbol_of_row(sym, sh, r);
 			if (pos <= 0) { dev_fail(err, DE_CHAIN_RANGE); id = REC_INVALID; }
 			else {
 				pos--;
@@ -574,10 +585,10 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_stream(const u32* __re
                                                                  StreamSpace sp, int* __restrict__ err)
 {
 	__shared__ AnchorTable anchors;
-	__shared__ i32 C[257];
+	__shared__ SymTable sym;
+	const int sh = sym_shift(n);
 	load_anchor_table(anchors, meta);
-	for (int i = threadIdx.x; i < 257; i += blockDim.x) C[i] = meta->ctable[i];
-	__syncthreads();
+	load_sym_table(sym, meta, sh);
 	const i32 idx = meta->idx;
 	const u32 nodes = S + N_ANCHOR;
 	const u32 lane = lane_id();
@@ -592,10 +603,14 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_stream(const u32* __re
 	for (;;) {
 		const u32 my = take_ticket_log(wt, !done && id == REC_INVALID, ticket, nodes, done, prev_batch, wgid, sp, err);
 		if (my != REC_INVALID) {
-			i32 bi = node_start(my, S, n, log2m, meta, idx);
-			if (bi >= 0 && my < S && is_anchor_row(anchors, bi + (bi >= idx ? 1 : 0))) bi = -1;
-			if (bi < 0) rec[my] = pack3(0, PR_NXT_INVALID, 0);
-			else { id = my; len = 0; v = ld_lf(lf + bi, pol_ld, false); }
+			const i32 bi = node_start(my, S, n, log2m, meta, idx);
+			bool live = bi >= 0;
+			if (live) {
+				v = ld_lf(lf + bi, pol_ld, false);
+				live = my >= S || (v & LF_ANCHOR) == 0;             // (duplicate of an anchor's sub-chain, as in k_inv_walk_len)
+			}
+			if (!live) rec[my] = pack3(0, PR_NXT_INVALID, 0);
+			else { id = my; len = 0; }
 		}
 		if (__ballot_sync(0xffffffffu, !done) == 0) break;
 		if (row == ST_ROWS) {                                   // this iteration opens a new chunk (warp-uniform)
@@ -614,9 +629,9 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_stream(const u32* __re
 			if (!stop) {
 				const i32 bi = row_to_byte(r, idx);
 				v = ld_lf(lf + bi, pol_ld, false);               // next gather goes out before the symbol search below
-				if (v & LF_MARK) { stop = true; nxt = node_of(anchors, r, bi, log2m, S); }
+				if (v & LF_MARK) { stop = true; nxt = node_of(anchors, v, r, bi, log2m, S); }
 			}
-			cp[row * 32 + lane] = (u8)symbol_of_row(C, r);
+			cp[row * 32 + lane] = (u8)symbol_of_row(sym, sh, r);
 			if (stop) {
 				if (len > PR_LEN_MAX) { dev_fail(err, DE_STREAM_OVERFLOW); len = PR_LEN_MAX; }
 				rec[id] = pack3(len, nxt, len);
