@@ -11,18 +11,22 @@
 //   lf[i]       = 1 + C[bwt[i]] + #{j < i : bwt[j] == bwt[i]} : the row of the suffix one position to the
 //               left. The symbol stepped over is NOT fetched from the BWT: it is the F-column symbol of
 //               lf[i], found in the 257-entry C table (shared memory). One random 32 B sector per byte.
-//   marks       bit 31 of lf[i] (row numbers need <= 31 bits, format.hpp:22) flags row(i) as the start of a
-//               sub-chain: one pseudo-random row in every window of m rows, plus the 120 rows the stored
-//               indices name (text positions k*step) and row 0 (text position nlen).
-//   pass 1      one walker per sub-chain start: walk left until the next mark; record (next start, length).
-//   ranking     asynchronous pointer jumping over the (next, length) records; the 121 anchors absorb. Every
+//   marks       bit 31 of lf[i] (row numbers need <= 30 bits, format.hpp:22) flags row(i) as the start of a
+//               sub-chain: one hashed row in every window of m rows, plus the 120 rows the stored indices name
+//               (text positions k*step) and row 0 (text position nlen) -- the anchors, which carry bit 30 as well.
+//   two-pass    (blocks under 30 Mi)
+//     pass 1    one walker per sub-chain start: walk left until the next mark; record (next start, length).
+//     ranking   asynchronous pointer jumping over the (next, length) records; the 121 anchors absorb. Every
 //               sub-chain learns which decode unit it belongs to and its offset from that unit's start, so all
 //               120 decode units of the format run concurrently, each cut into ~step/m independent pieces.
-//   pass 2      the same walk again, now writing bytes right-to-left at the known text offset, packed into
-//               aligned 32-bit stores.
+//     pass 2    the same walk again, now writing bytes right-to-left at the known text offset, packed into
+//               aligned 16-byte windows.
+//   single-walk (blocks of 30 Mi and more) the walk is done once: bytes are parked in per-warp streams, and after
+//               the ranking a replay of each warp's loop puts them in place (see "single-walk path" below).
 //
-// Device memory: caller's in (N+480) + out (N) + lf (4N) = 6N, plus o(N): 8 B per sub-chain (N/8 at m = 64)
-// and 1 KiB per 64 KiB tile (N/64).
+// Device memory: caller's in (N+480) + out (N) + lf (4N) = 6N, plus o(N): 8 B per sub-chain (N/2 at m = 16, kept in
+// the consumed input block) and 1 KiB per 64 KiB tile (N/64); the single-walk streams live in `out` and the free half
+// of `in`.
 #include "bwt_internal.cuh"
 #include <algorithm>
 
