@@ -17,7 +17,9 @@ The forward transform of the same block (configs[2]/[3] shape) is reported in th
             one sector per byte; `rand_peak` is the random
             32 B-sector gather rate measured live by the library's own micro-benchmark
   cpu_baseline  the unmodified reference (oracle/_ref) on this box's host cores, block-parallel like
-            Jampack::Compress/Decompress (jampack.cpp:215-219, :313-317): one block per core
+            Jampack::Compress/Decompress (jampack.cpp:215-219, :313-317): one block per core; `single_block` is the
+            other all-core shape (one block, Opt.Threads = cores); `value` is the better of the two
+  legacy_cuda_baseline  the reference's own CUDA inverse (bwt.cpp:8-19, :186-240), unmodified, in a child process
 
 --impl reference times only the reference CPU implementation (rank 0; other ranks exit).
 """
@@ -151,6 +153,48 @@ def cpu_reference(direction, block, fwd_out, cores, steps=1, warmup=0, budget_s=
     return {"value": round(P * n / sec / 1e6, 2), "unit": "MB/s", "cores": P, "kind": kind, "ms_per_step": round(sec * 1e3, 1),
             "steps": len(times), "output_matches": bool(ok),
             "sample": f"{P} x {n >> 20} MiB {direction} blocks, one per core (block-parallel, jampack.cpp:215-219), {len(times)} batch(es)"}
+
+
+def cpu_reference_single_block(direction, block, fwd_out, cores):
+    """Single-block shape (BASELINE.md plan item 4): ONE block with Opt.Threads = all cores. The inverse rounds that to
+    its unit table (bwt.cpp:116-132: >= 16 threads -> 120 units on 30 threads); the forward parallelises only sssort
+    (divsufsort.cpp:1491-1521) over the OpenMP default team."""
+    import oracle
+    ref = oracle.ref()
+    if ref is None:
+        return None
+    t0 = time.perf_counter()
+    if direction == "forward":
+        out = oracle.forward(block, "ref")
+        ok = bool((out == fwd_out).all())
+    else:
+        out = oracle.inverse(fwd_out, "ref", threads=cores)
+        ok = bool((out == block).all())
+    sec = time.perf_counter() - t0
+    return {"value": round(block.size / sec / 1e6, 2), "unit": "MB/s", "threads": cores, "output_matches": ok,
+            "sample": f"1 x {block.size >> 20} MiB {direction} block, Opt.Threads = {cores}"}
+
+
+def legacy_cuda_baseline(T, B):
+    """The reference's own CUDA inverse, in a child process with a timeout (see oracle/legacy_cuda.py)."""
+    import tempfile
+    from oracle import legacy_cuda
+    if not legacy_cuda.available():
+        return {"unavailable": "oracle/_ref/libjamref_cuda.so was not built (make -C oracle ref_cuda needs /root/reference and nvcc)"}
+    with tempfile.TemporaryDirectory() as d:
+        pb, pt = os.path.join(d, "B.npy"), os.path.join(d, "T.npy")
+        np.save(pb, B); np.save(pt, T)
+        try:
+            r = subprocess.run([sys.executable, "-m", "oracle.legacy_cuda", pb, pt, "2"], cwd=ROOT, capture_output=True, text=True, timeout=90)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": "legacy CUDA inverse did not finish within 90 s"}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"unavailable": f"legacy CUDA inverse failed (exit {r.returncode}): {(r.stderr or r.stdout).strip()[-200:]}"}
+    try:
+        return json.loads(lines[-1])
+    except ValueError:
+        return {"unavailable": "legacy CUDA inverse printed no result"}
 
 
 def run_reference(args, rank):
@@ -438,9 +482,18 @@ def main():
             cores = os.cpu_count() or 1
             cb = cpu_reference("inverse", T, B, cores)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "output_matches")}
+            line["cpu_baseline"]["single_block"] = cpu_reference_single_block("inverse", T, B, cores)   # the other all-core shape; `value` is the better one
+            sb = line["cpu_baseline"]["single_block"]
+            if sb and sb["value"] > line["cpu_baseline"]["value"]:
+                line["cpu_baseline"].update(value=sb["value"], sample=sb["sample"])
             if fwd:
                 cf = cpu_reference("forward", T, B, cores)
                 line["forward"]["cpu_baseline"] = {k: cf[k] for k in ("value", "unit", "cores", "kind", "sample", "output_matches")}
+                line["forward"]["cpu_baseline"]["single_block"] = cpu_reference_single_block("forward", T, B, cores)
+                sb = line["forward"]["cpu_baseline"]["single_block"]
+                if sb and sb["value"] > line["forward"]["cpu_baseline"]["value"]:
+                    line["forward"]["cpu_baseline"].update(value=sb["value"], sample=sb["sample"])
+            line["legacy_cuda_baseline"] = legacy_cuda_baseline(T, B)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
