@@ -3,6 +3,7 @@ declares, and refuses to compute without a GPU (no CPU path)."""
 import ctypes
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -103,3 +104,12 @@ def test_host_shims_compile_standalone(tmp_path):
     und = subprocess.run(["nm", "-u"] + objs, capture_output=True, text=True, check=True).stdout
     for s in ("jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_suffix_array", "jp_bwt_strerror"):
         assert s in und
+
+
+def test_missing_library_fails_loudly():
+    """No silent fallback when the CUDA library has not been built: the first call raises, naming the file."""
+    code = ("import jampack_b200 as jp, numpy as np\n"
+            "jp.LIB_PATH = '/nonexistent/libjpbwt.so'; jp._lib = None\n"
+            "try:\n    jp.forward(np.zeros(1000, dtype=np.uint8))\nexcept jp.BwtError as e:\n    print('RC', e.rc, 'libjpbwt.so' in str(e))\n")
+    r = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert "RC -2 True" in r.stdout, r.stdout + r.stderr
