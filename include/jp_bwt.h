@@ -66,7 +66,9 @@ int jp_bwt_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, in
 /* ---- the same stage with the block already resident in HBM ---------------------------------------
  * d_in / d_out are device pointers on `device`, both 16-byte aligned. The work is enqueued on
  * `stream` (a cudaStream_t, or NULL for the context's own stream) and the call returns after that stream
- * has drained. These are what the `value` leg of bench.py times, and what a device-resident
+ * has drained. The context's own stream is NON-BLOCKING: with stream == NULL the caller must have finished
+ * producing d_in (and must not be writing d_out) before the call -- work queued on the legacy default stream
+ * is not waited for. These are what the `value` leg of bench.py times, and what a device-resident
  * neighbour stage would call. */
 int jp_bwt_forward_device(const uint8_t* d_in, int32_t len, uint8_t* d_out, int device, void* stream);
 int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream);
