@@ -308,6 +308,138 @@ __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, 
 	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (region_log2 >= 32 || (v[i] >> region_log2) == region)) ISA[v[i]] = r[i];
 }
 
+// ---- 4b. run skip (JP_BWT_FWD_RUNSKIP=1; off by default until measured) --------------------------------
+// Prefix doubling pays one round per doubling of the longest repeat, and the cheapest way to make a long repeat is a
+// run of one symbol (zero pages, padding): a block of n equal bytes takes log2(n / depth) rounds over the whole block.
+// Runs have an exact shortcut. Let r(v) be the length of the run of T[v] that starts at v, and call v a RUN SUFFIX
+// when r(v) >= depth, the number of symbols in the initial key: its key is c^depth, so after the initial sort the run
+// suffixes of a symbol c form one group, and inside it suffix v = c^r(v) X(v), where X(v) starts with a symbol other
+// than c (or is empty). Comparing c^r X with c^r' X', r < r', is decided at position r: X's first symbol against c.
+// Hence the order inside the group is: first the suffixes whose run is followed by a SMALLER symbol (or by the end of
+// the text), by ascending r; then those followed by a larger one, by descending r; ties (equal class and r -- they
+// come from different runs) by the order of the X's. So
+//   * pass A (the first round, h = depth): a run suffix takes key2 = r (first class) or 2n + 1 - r (second class)
+//     instead of ISA[v + h] -- a block of equal bytes is sorted by that one pass -- which leaves its group with equal
+//     (class, r);
+//   * pass B (h still = depth) and every later round: a run suffix with r(v) >= h takes ISA[v + r(v)], the rank of
+//     X(v); one with r(v) < h the ordinary ISA[v + h]. Either way the key is uniform inside a group (its members have
+//     the same r) and the round leaves every suffix at least 2h-ordered, which is the invariant the ordinary keys of
+//     the NEXT round rely on when they read the rank of a position inside a run: c^r X keyed on an h-ordered rank of X
+//     is (r + h)-ordered, and r >= h. (Keying on ISA[v + r] regardless of h looks tempting and is wrong: a run suffix
+//     with r < h would then be less refined than its neighbours assume. Found by the emulated tests.)
+// All other suffixes are untouched. key2 needs one more bit (values up to 2n), which the host accounts for in
+// rank_bits. RL = r(v) for every position, `bits` = bitmap of the run suffixes (read through L2 by the gathers, so
+// only run suffixes pay for the RL gather).
+struct RunSkip { const u32* rl; const u32* bits; const u8* T; u32 first; };
+
+template <bool RS>
+__device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restrict__ ISA, const RunSkip& rs, int* __restrict__ err)
+{
+	if (RS) {
+		if ((__ldg(&rs.bits[v >> 5]) >> (v & 31)) & 1u) {
+			const u32 r = __ldg(&rs.rl[v]);                    // v + r <= n by construction
+			if (rs.first) {
+				const bool smaller_follows = (v + r >= n) || rs.T[v + r] < rs.T[v];
+				return smaller_follows ? r : 2u * n + 1u - r;
+			}
+			if (r >= h) return __ldg(&ISA[v + r]);
+		}
+	}
+	u32 p = v + h;
+	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+	return __ldg(&ISA[p]);
+}
+
+constexpr int RUN_TILE = 2048;
+constexpr u32 RUN_NONE = 0xffffffffu;
+__device__ __forceinline__ u32 warp_min_u32(u32 v)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// last position of the first run that ENDS inside the tile (T[j] != T[j+1], or j == n-1); RUN_NONE if none does
+__global__ void __launch_bounds__(256) k_run_first(const u8* __restrict__ T, u32 n, u32* __restrict__ tile_first)
+{
+	__shared__ u32 wbest[8];
+	const u32 base = blockIdx.x * RUN_TILE;
+	u32 best = RUN_NONE;
+	#pragma unroll
+	for (int i = 0; i < RUN_TILE / 256; i++) {
+		const u32 j = base + i * 256 + threadIdx.x;
+		if (j < n && (j == n - 1 || T[j] != T[j + 1])) best = min(best, j);
+	}
+	best = warp_min_u32(best);
+	if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		#pragma unroll
+		for (int k = 1; k < 8; k++) best = min(best, wbest[k]);
+		tile_first[blockIdx.x] = best;
+	}
+}
+
+// single block: tile_next[t] = first run end in any LATER tile (exclusive suffix minimum)
+__global__ void __launch_bounds__(1024) k_run_scan(const u32* __restrict__ tile_first, u32 tiles, u32* __restrict__ tile_next)
+{
+	__shared__ u32 part[1024];
+	const u32 t = threadIdx.x;
+	const u32 per = (tiles + 1023) / 1024;
+	const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	u32 m = RUN_NONE;
+	for (u32 k = lo; k < hi; k++) m = min(m, tile_first[k]);
+	part[t] = m;
+	__syncthreads();
+	u32 run = RUN_NONE;
+	for (u32 k = t + 1; k < 1024; k++) run = min(run, part[k]);
+	for (u32 k = hi; k > lo; k--) { tile_next[k - 1] = run; run = min(run, tile_first[k - 1]); }
+}
+
+// RL[j] = length of the run of T[j] starting at j; bits = (RL[j] >= depth); *count += number of run suffixes
+__global__ void __launch_bounds__(256) k_run_fill(const u8* __restrict__ T, u32 n, const u32* __restrict__ tile_next, u32 depth,
+                                                  u32* __restrict__ RL, u32* __restrict__ bits, u32* __restrict__ count)
+{
+	__shared__ u32 end_at[RUN_TILE];            // first run end at or after each position of the tile
+	__shared__ u32 wfirst[8];
+	const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const u32 base = blockIdx.x * RUN_TILE;
+	// each thread owns 8 consecutive positions: its first run end, if any
+	u32 mine = RUN_NONE;
+	#pragma unroll
+	for (int k = 7; k >= 0; k--) {
+		const u32 j = base + t * 8 + k;
+		if (j < n && (j == n - 1 || T[j] != T[j + 1])) mine = j;
+	}
+	// exclusive suffix minimum over the threads: inside the warp by shuffles, across the 8 warps through shared memory
+	u32 incl = mine;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl = min(incl, x); }
+	u32 excl = __shfl_down_sync(0xffffffffu, incl, 1);
+	if (lane == 31) excl = RUN_NONE;
+	if (lane == 0) wfirst[w] = incl;
+	__syncthreads();
+	u32 carry = min(tile_next[blockIdx.x], excl);
+	for (u32 k = 7; k > w; k--) carry = min(carry, wfirst[k]);
+	#pragma unroll
+	for (int k = 7; k >= 0; k--) {
+		const u32 j = base + t * 8 + k;
+		if (j < n && (j == n - 1 || T[j] != T[j + 1])) carry = j;
+		end_at[t * 8 + k] = carry;
+	}
+	__syncthreads();
+	u32 cnt = 0;
+	#pragma unroll
+	for (int i = 0; i < RUN_TILE / 256; i++) {
+		const u32 j = base + i * 256 + t;
+		u32 r = 0;
+		if (j < n) { r = end_at[i * 256 + t] - j + 1; RL[j] = r; }
+		const u32 m = __ballot_sync(0xffffffffu, j < n && r >= depth);
+		if (lane == 0 && base + i * 256 + (t & ~31u) < n) { bits[(base + i * 256 + t) >> 5] = m; cnt += __popc(m); }
+	}
+	if (lane == 0 && cnt) atomicAdd(count, cnt);
+}
+
 // ---- 5a. doubling round, small groups: gather + segmented sort in shared memory -------------------------
 // Groups are contiguous in the active set, so refining them is a SEGMENTED sort. Block c owns the groups whose
 // head lies in its window of SG_WIN slots; they end within two windows unless the last one is "large". The block
@@ -386,11 +518,12 @@ __device__ __forceinline__ u32 warp_rev_incl_min(u32 v)
 // scans (last head at or before me / first group end at or after me) stitched across the block through a small
 // table with a single barrier; then it counts the members of its group that sort before it.
 constexpr size_t SG_SMEM_LIGHT = (size_t)SG_CAP * (4 + 4 + 1);
+template <bool RS>
 __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
                                                          const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
                                                          u8* __restrict__ F, u32* __restrict__ counters /*[2]=has_large [3]=queued*/,
                                                          u32* __restrict__ queue, u32* __restrict__ win_first, u32* __restrict__ win_large,
-                                                         int* __restrict__ err)
+                                                         int* __restrict__ err, RunSkip rs)
 {
 	extern __shared__ __align__(16) u8 sg_smem[];
 	u32* skey = reinterpret_cast<u32*>(sg_smem);        // key2 = ISA[s + h]; later the refined suffix ids
@@ -416,10 +549,8 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restric
 			const u64 g = K[j] >> rank_bits;
 			const bool head = (e == 0) || (K[j - 1] >> rank_bits) != g;
 			const bool last = (e == len - 1) || (K[j + 1] >> rank_bits) != g;
-			u32 p = v + h;
-			if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
 			sval[e] = v;
-			skey[e] = __ldg(&ISA[p]);
+			skey[e] = key2_of<RS>(v, h, n, ISA, rs, err);
 			hl = (head ? 1u : 0u) | (last ? 2u : 0u) | 4u;
 		}
 		const u32 f = warp_incl_max((hl & 1u) ? (i32)e : 0);
@@ -485,9 +616,10 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restric
 }
 
 // Radix route for the queued tiles: LSD radix sort of (local group id, key2) that never leaves shared memory.
+template <bool RS>
 __global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
                                                                const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
-                                                               u8* __restrict__ F, const u32* __restrict__ queue, int* __restrict__ err)
+                                                               u8* __restrict__ F, const u32* __restrict__ queue, int* __restrict__ err, RunSkip rs)
 {
 	extern __shared__ __align__(16) u8 sg_smem[];
 	u64* skey = reinterpret_cast<u64*>(sg_smem);
@@ -509,10 +641,9 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __rest
 			if (e < len) {
 				const u32 j = start + e;
 				const u32 v = V[j];
-				u32 p = v + h;
-				if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
+				const u32 k2 = key2_of<RS>(v, h, n, ISA, rs, err);
 				sval[e] = v;
-				skey[e] = (((K[j] >> rank_bits) - g0) << 32) | (u64)__ldg(&ISA[p]);
+				skey[e] = (((K[j] >> rank_bits) - g0) << 32) | (u64)k2;
 			}
 		}
 		__syncthreads();
@@ -628,17 +759,17 @@ __device__ __forceinline__ u32 large_group_of(const u32* __restrict__ lg_off, u3
 	return lo;
 }
 
+template <bool RS>
 __global__ void __launch_bounds__(256) k_large_extract(const u32* __restrict__ V, const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
                                                        const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 ng, u32 total,
-                                                       u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err)
+                                                       u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err, RunSkip rs)
 {
 	const u32 x = blockIdx.x * 256 + threadIdx.x;
 	if (x >= total) return;
 	const u32 g = large_group_of(lg_off, ng, x);
 	const u32 v = V[lg_head[g] + (x - lg_off[g])];
-	u32 p = v + h;
-	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
-	LK[x] = ((u64)g << rank_bits) | (u64)__ldg(&ISA[p]);
+	const u32 k2 = key2_of<RS>(v, h, n, ISA, rs, err);
+	LK[x] = ((u64)g << rank_bits) | (u64)k2;
 	LV[x] = v;
 }
 
@@ -657,14 +788,13 @@ __global__ void __launch_bounds__(256) k_large_writeback(const u64* __restrict__
 }
 
 // ---- 5c. doubling round, composite-key route for the whole active set (A/B reference: JP_BWT_FWD_GLOBAL=1) ---------------------------------------------------
+template <bool RS>
 __global__ void __launch_bounds__(256) k_fwd_gather(u64* __restrict__ K, const u32* __restrict__ V, u32 A,
-                                                    const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err)
+                                                    const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err, RunSkip rs)
 {
 	const u32 j = blockIdx.x * 256 + threadIdx.x;
 	if (j >= A) return;
-	u32 p = V[j] + h;
-	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
-	K[j] |= (u64)__ldg(&ISA[p]);
+	K[j] |= (u64)key2_of<RS>(V[j], h, n, ISA, rs, err);
 }
 
 // ---- 6. emission ---------------------------------------------------------------------------------------
@@ -709,6 +839,7 @@ struct FwdBuffers {
 	RadixBuffers rb;
 	u32* P[2];
 	u32* ISA; u32* SA; u32* R;
+	u32* RL; u32* run_bits; u32* run_first; u32* run_next; u32* run_count;   // run skip (null when off)
 	int isa_region_log2;
 	u8* F;
 	u32* queue;
@@ -719,6 +850,12 @@ struct FwdBuffers {
 	int* err;
 };
 
+static bool runskip_enabled()
+{
+	const char* e = getenv("JP_BWT_FWD_RUNSKIP");
+	return e != nullptr && atoi(e) != 0;
+}
+
 static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 {
 	const size_t N = (size_t)n;
@@ -726,6 +863,9 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + 2 * Arena::align(N * 4) +
 	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) + Arena::align(N + 64) + Arena::align(gtiles * sizeof(GAgg)) +
 	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + 5 * Arena::align((N / SG_WIN + 16) * 4);
+	const bool runskip = runskip_enabled();
+	const size_t run_tiles = (N + RUN_TILE - 1) / RUN_TILE;
+	if (runskip) total += Arena::align(N * 4) + Arena::align((N / 32 + 2) * 4) + 2 * Arena::align((run_tiles + 1) * 4) + Arena::align(64);
 	JP_TRY(arena_reserve(c, total));
 	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
 	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
@@ -750,6 +890,12 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	b.counters = arena_take<u32>(c, 16);
 	b.err = arena_take<int>(c, 16);
 	b.rb.err = b.err;
+	b.RL = b.run_bits = b.run_first = b.run_next = b.run_count = nullptr;
+	if (runskip) {
+		b.RL = arena_take<u32>(c, N); b.run_bits = arena_take<u32>(c, N / 32 + 2);
+		b.run_first = arena_take<u32>(c, run_tiles + 1); b.run_next = arena_take<u32>(c, run_tiles + 1);
+		b.run_count = arena_take<u32>(c, 16);
+	}
 	return JP_OK;
 }
 
@@ -808,18 +954,32 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
 	                                                         rs_stride((u32)radix_tiles((size_t)n))); JP_LAUNCH(c);
 	JP_KCHECK();
+	const bool runskip = b.RL != nullptr;                                // JP_BWT_FWD_RUNSKIP=1 (see "run skip" above)
+	if (runskip) {
+		const u32 run_tiles = (u32)(((size_t)n + RUN_TILE - 1) / RUN_TILE);
+		JP_CUDA(cudaMemsetAsync(b.run_count, 0, 64, s));
+		k_run_first<<<run_tiles, 256, 0, s>>>(d_T, (u32)n, b.run_first); JP_LAUNCH(c);
+		k_run_scan<<<1, 1024, 0, s>>>(b.run_first, run_tiles, b.run_next); JP_LAUNCH(c);
+		k_run_fill<<<run_tiles, 256, 0, s>>>(d_T, (u32)n, b.run_next, (u32)depth, b.RL, b.run_bits, b.run_count); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaMemcpyAsync(c.h_small + 14, b.run_count, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the first group step's sync
+	}
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
-	if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_seg_sort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
+	if (cudaFuncSetAttribute(k_seg_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
 	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/true);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
 
-	const int rank_bits = bit_length((u64)n);
+	const int rank_bits = bit_length(runskip ? 2 * (u64)n + 1 : (u64)n);   // key2 is a rank <= n, or a run key <= 2n
 	int pc = 0;
 	JP_TRY(group_step(c, b, cur, pc, true, false, (u32)n, rank_bits, s));
+	const bool use_rs = runskip && c.h_small[14] != 0;                   // no run suffix in this block: the plain kernels
+	RunSkip rs; rs.rl = b.RL; rs.bits = b.run_bits; rs.T = d_T; rs.first = 1;
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	int act = cur ^ 1; pc ^= 1;
 	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
@@ -831,6 +991,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	while (A > 0) {
 		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
+		rs.first = rounds == 0 ? 1u : 0u;                                // run skip: pass A, then pass B at the same h
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
 		st->active_fraction[rounds] = (float)((double)A / (double)n);
 		sectors += 2ull * A;
@@ -842,16 +1003,22 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			// shared-memory radix kernel; groups longer than a window are reported for the large-group route
 			const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
 			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
-			k_seg_sort<<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
-			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err); JP_LAUNCH(c);
+			if (use_rs) k_seg_sort<true><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
+			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err, rs);
+			else k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
+			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err, rs);
+			JP_LAUNCH(c);
 			JP_KCHECK();
 			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 			JP_CUDA(cudaStreamSynchronize(s));
 			const bool large = c.h_small[10] != 0;
 			const u32 queued = (u32)c.h_small[11];
 			if (queued) {
-				k_seg_sort_radix<<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
-				                                                    rank_bits, b.F, b.queue, b.err); JP_LAUNCH(c);
+				if (use_rs) k_seg_sort_radix<true><<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
+				                                                    rank_bits, b.F, b.queue, b.err, rs);
+				else k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
+				                                                    rank_bits, b.F, b.queue, b.err, rs);
+				JP_LAUNCH(c);
 				JP_KCHECK();
 				st->ms_phase[6] += (float)queued;       // tiles that needed the shared-memory radix route
 			}
@@ -868,8 +1035,11 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 				RadixBuffers lb = b.rb;
 				lb.k[0] = b.rb.k[act ^ 1]; lb.k[1] = b.rb.k[act];
 				lb.v[0] = b.rb.v[act ^ 1]; lb.v[1] = b.R;
-				k_large_extract<<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
-				                                                    lb.k[0], lb.v[0], b.err); JP_LAUNCH(c);
+				if (use_rs) k_large_extract<true><<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
+				                                                    lb.k[0], lb.v[0], b.err, rs);
+				else k_large_extract<false><<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
+				                                                    lb.k[0], lb.v[0], b.err, rs);
+				JP_LAUNCH(c);
 				const int key_bits = rank_bits + bit_length((u64)(ng - 1));
 				const int lc = radix_sort_pairs(lb, 0, total, 0, key_bits, s, &c.launches);
 				if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
@@ -881,7 +1051,9 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		} else {
 			st->ms_phase[5] += (float)((double)A / (double)n);
 			large_frac_now = G * (u64)SG_WIN >= A ? 0.0 : 1.0;       // back to the segmented route once groups average under a window
-			k_fwd_gather<<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err); JP_LAUNCH(c);
+			if (use_rs) k_fwd_gather<true><<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err, rs);
+			else k_fwd_gather<false><<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err, rs);
+			JP_LAUNCH(c);
 			const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
 			cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
 			if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
@@ -896,7 +1068,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		act = cur ^ 1; pc ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
 		large_frac_prev = large_frac_now;
-		h *= 2; rounds++;
+		if (!(use_rs && rounds == 0)) h *= 2;
+		rounds++;
 	}
 	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
 	JP_CUDA(cudaEventRecord(c.ev[4], s));

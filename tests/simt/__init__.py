@@ -43,6 +43,7 @@ def lib():
         L = C.CDLL(build())
         L.emu_inverse.argtypes = [_u8p, C.c_int32, _u8p, C.c_int, _i32p, _i32p]
         L.emu_forward.argtypes = [_u8p, C.c_int32, _u8p, _i32p, _i32p]
+        L.emu_suffix_array.argtypes = [_u8p, C.c_int32, _i32p]
         _lib = L
     return _lib
 
@@ -64,3 +65,11 @@ def forward(T, prefill=0x5C):
     r, la = C.c_int32(0), C.c_int32(0)
     rc = lib().emu_forward(T.ctypes.data_as(_u8p), T.size, out.ctypes.data_as(_u8p), C.byref(r), C.byref(la))
     return rc, out, r.value, la.value
+
+
+def suffix_array(T):
+    """-> (rc, SA) of the emulated suffix sorter (jp::debug_suffix_array)"""
+    T = np.ascontiguousarray(T, dtype=np.uint8)
+    sa = np.zeros(max(T.size, 1), dtype=np.int32)
+    rc = lib().emu_suffix_array(T.ctypes.data_as(_u8p), T.size, sa.ctypes.data_as(_i32p))
+    return rc, sa[: T.size]

@@ -59,6 +59,12 @@ int emu_inverse(const uint8_t* in, int32_t len_with_trailer, uint8_t* out, int c
 	return rc;
 }
 
+int emu_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
+{
+	jp::Ctx& c = jp::ctx();
+	return jp::debug_suffix_array(c, in, n, sa);
+}
+
 int emu_forward(const uint8_t* in, int32_t len, uint8_t* out, int32_t* rounds, int32_t* launches)
 {
 	jp::Ctx& c = jp::ctx();
