@@ -148,3 +148,13 @@ def test_emulated_forward_with_run_skip(emu, orc, name):
     assert rc1 == 0 and (got1 == want).all()
     if name in ("all_a", "zero_page_in_noise", "three_plateaus"):
         assert rounds1 <= 2 < rounds0, (rounds0, rounds1)      # one pass over the runs instead of log2(run / depth) rounds
+
+
+@pytest.mark.parametrize("kind,n,seed", [("kat_extremes", 2, 0), ("uniform", 3, 1), ("alla", 1000, 0), ("markov2", 3000, 2), ("repetitive", 5000, 3)])
+def test_emulated_suffix_array(emu, orc, kind, n, seed):
+    """jp::debug_suffix_array (the sorter behind jp_bwt_suffix_array / the -m2 shim) against a brute-force sort."""
+    T = orc.gen(kind, n, seed)
+    rc, sa = emu.suffix_array(T)
+    b = T.tobytes()
+    assert rc == 0
+    assert sa.tolist() == sorted(range(n), key=lambda i: b[i:])
