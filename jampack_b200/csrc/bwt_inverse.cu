@@ -163,7 +163,10 @@ __global__ void __launch_bounds__(256) k_inv_ctable(const u32* __restrict__ bin_
 // coalesced 128 B rows of 32-bit words and re-distributed by shuffle so that lane l handles byte
 // 32*k + l of the row (text order == lane order). Equal bytes inside a warp step are ranked with
 // match.any; running per-warp counters live in shared memory; LF values leave as 128 B coalesced rows.
-__global__ void __launch_bounds__(INV_THREADS, 3) k_inv_lf(const u8* __restrict__ bwt, i32 n,
+// MINB = resident blocks per SM asked of the compiler: 3 (80 registers) is the measured configuration; 4 caps the
+// kernel at 64 registers with 16 bytes of spill -- JP_BWT_INV_LF_BLOCKS=4 selects it, to be measured.
+template <int MINB>
+__global__ void __launch_bounds__(INV_THREADS, MINB) k_inv_lf(const u8* __restrict__ bwt, i32 n,
                                                         const u32* __restrict__ tile_excl, const InvMeta* __restrict__ meta,
                                                         u32* __restrict__ lf, int log2m)
 {
@@ -772,6 +775,12 @@ static int pick_log2m(i32 nlen)
 	return nlen >= (1 << 22) ? 4 : 3;
 }
 
+static int lf_blocks_per_sm()
+{
+	const char* e = getenv("JP_BWT_INV_LF_BLOCKS");
+	return (e && atoi(e) == 4) ? 4 : 3;
+}
+
 static int walk_flags()
 {
 	if (const char* e = getenv("JP_BWT_INV_FLAGS")) return atoi(e);
@@ -903,7 +912,9 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	JP_TRY(inv_alloc(c, nlen, b, scratch_in, d_out));
 	JP_TRY(inv_build_table(c, d_in, len, nlen, d_out, b, s));
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
-	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
+	if (lf_blocks_per_sm() == 4) k_inv_lf<4><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m);
+	else k_inv_lf<3><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m);
+	JP_LAUNCH(c);
 	k_inv_mark_anchors<<<1, 128, 0, s>>>(b.meta, b.lf, nlen); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
@@ -997,7 +1008,7 @@ int debug_lf(Ctx& c, const u8* h_in, i32 nlen, i32* h_lf, i32* h_ctable)
 		JP_CUDA(cudaStreamSynchronize(s));
 	}
 	JP_TRY(inv_build_table(c, d_in, nlen, nlen, d_out, b, s));
-	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
+	k_inv_lf<3><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
 	k_strip_marks<<<(nlen + 255) / 256, 256, 0, s>>>(b.lf, nlen); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(h_lf, b.lf, (size_t)nlen * 4, cudaMemcpyDeviceToHost, s));
