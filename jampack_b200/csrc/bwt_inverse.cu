@@ -531,33 +531,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_emit(const u32* __rest
 //   * Tail rows (lanes idle while the warp's last sub-chains finish) are the overhead: ~25 % of nlen for 64 MiB.
 //     If the chunk space or a length field overflows, DE_STREAM_OVERFLOW is raised and the host reruns the
 //     two-pass path on the intact LF table.
-constexpr int ST_ROWS  = 32;
-constexpr int ST_CHUNK = ST_ROWS * 32;           // bytes per stream chunk
-constexpr int ST_AHEAD = 8;                      // rows before a chunk fills at which the next one is requested
-constexpr int PR_DIST_BITS = 24, PR_NXT_BITS = 26;
-constexpr u32 PR_DIST_MASK = (1u << PR_DIST_BITS) - 1, PR_NXT_MASK = (1u << PR_NXT_BITS) - 1;
-constexpr u32 PR_NXT_INVALID = PR_NXT_MASK;
-constexpr u32 PR_LEN_MAX = (1u << (64 - PR_DIST_BITS - PR_NXT_BITS)) - 1;
-constexpr u32 ST_NONE = 0xffffffffu;
-
-__device__ __forceinline__ u64 pack3(u32 len, u32 nxt, u32 dist) { return ((u64)len << (PR_DIST_BITS + PR_NXT_BITS)) | ((u64)nxt << PR_DIST_BITS) | dist; }
-__device__ __forceinline__ u32 pr_len(u64 r)  { return (u32)(r >> (PR_DIST_BITS + PR_NXT_BITS)); }
-__device__ __forceinline__ u32 pr_nxt(u64 r)  { return (u32)(r >> PR_DIST_BITS) & PR_NXT_MASK; }
-__device__ __forceinline__ u32 pr_dist(u64 r) { return (u32)r & PR_DIST_MASK; }
-
-struct StreamSpace {
-	u8* base0; u32 cap0;           // chunks [0, cap0) live here (the output block) ...
-	u8* base1; u32 cap1;           // ... chunks [cap0, cap0 + cap1) here (free part of the consumed input, or workspace)
-	u32* chunk_head;               // [walker warp] first chunk of the warp's stream
-	u32* chunk_next;               // [chunk] the chunk that follows in the same stream
-	u32* batch_head;               // [walker warp] first ticket batch the warp drew (batch = base / WALK_BATCH)
-	u32* batch_next;               // [batch] the batch the same warp drew next
-	u32  batch_cap;
-};
-__device__ __forceinline__ u8* chunk_ptr(const StreamSpace& sp, u32 c)
-{
-	return c < sp.cap0 ? sp.base0 + (size_t)c * ST_CHUNK : sp.base1 + (size_t)(c - sp.cap0) * ST_CHUNK;
-}
+#include "inv_stream.cuh"
 
 // take_ticket, with the batch bases logged per warp (prev_batch is lane 0's)
 __device__ __forceinline__ u32 take_ticket_log(WarpTickets& wt, bool need, u32* __restrict__ ticket, u32 nodes, bool& done,
@@ -765,6 +739,16 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 
 	}
 }
 
+// ---- single-walk path, several sub-chains per walker thread: declarations (the kernels are at the end of the file) ----
+constexpr int ILP_THREADS = 128;
+constexpr int ILP_WARPS   = ILP_THREADS / 32;
+template <int NS>
+__global__ void k_inv_walk_stream_ilp(const u32* __restrict__ lf, const InvMeta* __restrict__ meta, i32 n, int log2m, u32 S, u64* __restrict__ rec,
+                                      u32* __restrict__ ticket, u32* __restrict__ chunk_ctr, StreamSpace sp, int* __restrict__ err);
+// the replay kernel of this variant lives in bwt_inverse_ilp.cu (a second copy of the replay loop in this translation unit
+// changes the schedule nvcc picks for k_inv_place; the measured kernels are to stay bit-identical)
+void launch_inv_place_ilp4(int blocks, cudaStream_t s, i32 n, i32 step, u32 S, const u64* rec, StreamSpace sp, u8* out, int* err);
+
 // ---- host driver -----------------------------------------------------------------------------------
 // Marker spacing m. A pass costs about nlen / (gather rate) + (longest sub-chain) * (unloaded DRAM latency), and
 // the longest of nlen/m geometric sub-chains is ~ m * ln(nlen/m): measured on 64 MiB, m = 64 / 32 / 16 give
@@ -798,6 +782,7 @@ struct InvBuffers {
 	u32* lf; u32* tile_hist; u32* bin_total; InvMeta* meta; u64* rec; u32* ticket; int* err;
 	int tiles; int log2m; u32 S;
 	bool single;                  // single-walk path (k_inv_walk_stream / k_inv_place)
+	int  ilp;                     // sub-chains per walker thread: 1, or 4 (JP_BWT_INV_ILP=4: the *_ilp kernels, ILP_THREADS wide)
 	int  wblocks;                 // walker blocks of the single-walk kernels (the replay needs the same grid)
 	StreamSpace sp;
 };
@@ -829,6 +814,22 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 	size_t extra_stream = 0, in_free_off = 0, in_free = 0;
 	b.wblocks = 0;
 	b.sp = StreamSpace{};
+	b.ilp = 1;
+	if (const char* e = getenv("JP_BWT_INV_ILP")) if (atoi(e) == 4) b.ilp = 4;
+	const size_t chunk_bytes = (size_t)ST_CHUNK * b.ilp;            // 32 rows of 32 * ilp bytes
+	const int wthreads = b.ilp > 1 ? ILP_THREADS : INV_THREADS;
+	if (b.single && b.ilp > 1) {
+		int per_sm = 2;                                               // 2 x 4 warps x 32 lanes x 4 sub-chains = 1024 gathers in flight per SM
+		if (const char* e = getenv("JP_BWT_INV_WBLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
+		b.wblocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)per_sm * c.sm_count, nodes / ((size_t)wthreads * b.ilp * 8)));
+		if (rec_in_input) {
+			in_free_off = (nodes * 8 + 15) & ~(size_t)15;
+			in_free = (size_t)nlen > in_free_off ? (size_t)nlen - in_free_off : 0;
+		} else extra_stream = (size_t)nlen / 2;
+		if (mode == 1) extra_stream += (size_t)nlen / 2 + (size_t)b.wblocks * (wthreads / 32) * 160 * 32 * b.ilp;
+		b.sp.cap0 = (u32)((size_t)nlen / chunk_bytes);
+		b.sp.batch_cap = (u32)(nodes / WALK_BATCH + (size_t)b.wblocks * (wthreads / 32) * 4 * b.ilp + 16);
+	} else
 	if (b.single) {
 		// every lane should see a handful of sub-chains, or the tail rows dominate the stream
 		// (measured on 64 MiB: 8 / 6 / 5 / 4 / 3 blocks per SM walk in 1.154 / 1.142 / 1.146 / 1.173 / 1.388 ms and leave
@@ -847,12 +848,12 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 		b.sp.cap0 = (u32)((size_t)nlen / ST_CHUNK);
 		b.sp.batch_cap = (u32)(nodes / WALK_BATCH + (size_t)b.wblocks * INV_WARPS * 4 + 16);
 	}
-	const size_t walker_warps = (size_t)b.wblocks * INV_WARPS;
+	const size_t walker_warps = (size_t)b.wblocks * (wthreads / 32);
 	if (const char* e = getenv("JP_BWT_INV_STREAM_CAP")) {          // tests: shrink the stream space to provoke the two-pass rerun
 		const long v = atol(e);
 		if (b.single && v >= 0 && (u32)v < b.sp.cap0) { b.sp.cap0 = (u32)v; in_free = 0; extra_stream = 0; }
 	}
-	const u32 cap_in = (u32)(in_free / ST_CHUNK), cap_extra = (u32)(extra_stream / ST_CHUNK);
+	const u32 cap_in = (u32)(in_free / chunk_bytes), cap_extra = (u32)(extra_stream / chunk_bytes);
 	if (b.single) {
 		// region 1 is ONE address range: the free part of the input when there is no top-up, else the workspace piece
 		// alone (the input's free part is then left unused -- only tests and the non-consuming entry point get here)
@@ -860,7 +861,7 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 	}
 	size_t total = Arena::align((size_t)nlen * 4) + Arena::align((size_t)b.tiles * 256 * 4) + Arena::align(256 * 4) +
 	               Arena::align(sizeof(InvMeta)) + (rec_in_input ? 0 : Arena::align(nodes * 8)) + Arena::align(64) + Arena::align(64);
-	if (b.single) total += Arena::align((size_t)cap_extra * ST_CHUNK) + 2 * Arena::align(walker_warps * 4) +
+	if (b.single) total += Arena::align((size_t)cap_extra * chunk_bytes) + 2 * Arena::align(walker_warps * 4) +
 	                       Arena::align(((size_t)b.sp.cap0 + b.sp.cap1) * 4) + Arena::align((size_t)b.sp.batch_cap * 4);
 	JP_TRY(arena_reserve(c, total));
 	b.lf = arena_take<u32>(c, (size_t)nlen);
@@ -872,7 +873,7 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 	b.err = arena_take<int>(c, 16);
 	if (b.single) {
 		b.sp.base0 = d_out;
-		b.sp.base1 = cap_extra > 0 ? arena_take<u8>(c, (size_t)cap_extra * ST_CHUNK) : scratch_in + in_free_off;
+		b.sp.base1 = cap_extra > 0 ? arena_take<u8>(c, (size_t)cap_extra * chunk_bytes) : scratch_in + in_free_off;
 		b.sp.chunk_head = arena_take<u32>(c, walker_warps);
 		b.sp.batch_head = arena_take<u32>(c, walker_warps);
 		b.sp.chunk_next = arena_take<u32>(c, (size_t)b.sp.cap0 + b.sp.cap1);
@@ -929,21 +930,25 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		// (serialising the walks of the blocks in flight on one GPU behind a host-side gate, so that the other blocks'
 		// table builds, rankings and placements could fill in beside a single DRAM-bound walk, was measured: 35.3-35.6
 		// against 35.7-36.0 GB/s with four blocks in flight -- the hardware's own interleaving is as good)
-		k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err); JP_LAUNCH(c);
+		if (b.ilp == 4) k_inv_walk_stream_ilp<4><<<b.wblocks, ILP_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
+		else k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
+		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
 		k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap); JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);
-		k_inv_place<<<b.wblocks, INV_THREADS, 0, s>>>(nlen, step, b.S, b.rec, b.sp, text, b.err); JP_LAUNCH(c);
+		if (b.ilp == 4) launch_inv_place_ilp4(b.wblocks, s, nlen, step, b.S, b.rec, b.sp, text, b.err);
+		else k_inv_place<<<b.wblocks, INV_THREADS, 0, s>>>(nlen, step, b.S, b.rec, b.sp, text, b.err);
+		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaMemcpyAsync(d_out, text, (size_t)nlen, cudaMemcpyDeviceToDevice, s));   // (meaningless but harmless after a failure)
 		JP_CUDA(cudaEventRecord(c.ev[5], s));
 		JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
 		JP_CUDA(cudaMemcpyAsync(c.h_small + 4, b.ticket + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));
 		JP_CUDA(cudaStreamSynchronize(s));
-		st->stream_chunks = (i32)std::min<u32>((u32)c.h_small[4], 0x7fffffffu);
+		st->stream_chunks = (i32)std::min<u64>((u64)(u32)c.h_small[4] * (u64)b.ilp, 0x7fffffffull);   // in KiB whatever the chunk size
 		st->random_sectors = (u64)nlen;
 		if (c.h_small[0] == DE_STREAM_OVERFLOW) {                           // rare: rerun on the intact LF table
 			two_pass = true;
@@ -1067,5 +1072,96 @@ double debug_gather_rate(Ctx& c, u64 table_bytes, i32 chains, i32 steps, int dep
 	}
 	return (double)blocks * 256.0 * (double)steps / ((double)best * 1e-3);
 }
+
+// ---- single-walk path, several sub-chains per walker thread (JP_BWT_INV_ILP=4; off by default, to be measured) ----
+// Same algorithm, different shape: every lane interleaves NS sub-chains, so a warp keeps 32 * NS gathers in flight and
+// a walk saturates DRAM from a quarter of the warps (and of the registers) the one-chain-per-lane kernel holds for its
+// whole duration -- room in which the issue-bound kernels of OTHER blocks in flight can run beside it.
+// A stream row is now lane x slot (NS * 32 bytes, slot-major), a chunk 32 rows; tickets are drawn slot by slot, which
+// the replay repeats literally. Blocks are ILP_THREADS wide in both kernels (the replay stages a whole chunk per warp).
+
+template <int NS>
+__global__ void __launch_bounds__(ILP_THREADS) k_inv_walk_stream_ilp(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
+                                                                     i32 n, int log2m, u32 S, u64* __restrict__ rec,
+                                                                     u32* __restrict__ ticket, u32* __restrict__ chunk_ctr,
+                                                                     StreamSpace sp, int* __restrict__ err)
+{
+	constexpr u32 ROW = 32u * NS, CHUNK = ST_ROWS * ROW;
+	__shared__ AnchorTable anchors;
+	__shared__ SymTable sym;
+	const int sh = sym_shift(n);
+	load_anchor_table(anchors, meta);
+	load_sym_table(sym, meta, sh);
+	const i32 idx = meta->idx;
+	const u32 nodes = S + N_ANCHOR;
+	const u32 lane = lane_id();
+	const u32 wgid = blockIdx.x * ILP_WARPS + (threadIdx.x >> 5);
+	const u32 cap = sp.cap0 + sp.cap1;
+	const u64 pol_ld = policy_evict_first();
+	WarpTickets wt = {0, 0};
+	u32 id[NS], v[NS], len[NS];
+	#pragma unroll
+	for (int k = 0; k < NS; k++) { id[k] = REC_INVALID; v[k] = 0; len[k] = 0; }
+	u32 prev_batch = ST_NONE, chunk = ST_NONE, nextc = 0, row = ST_ROWS;
+	u8* cp = nullptr;
+	bool done = false;
+	for (;;) {
+		bool any_live = false;
+		#pragma unroll
+		for (int k = 0; k < NS; k++) {
+			const u32 my = take_ticket_log(wt, !done && id[k] == REC_INVALID, ticket, nodes, done, prev_batch, wgid, sp, err);
+			if (my != REC_INVALID) {
+				const i32 bi = node_start(my, S, n, log2m, meta, idx);
+				bool live = bi >= 0;
+				if (live) {
+					v[k] = ld_lf(lf + bi, pol_ld, false);
+					live = my >= S || (v[k] & LF_ANCHOR) == 0;
+				}
+				if (!live) rec[my] = pack3(0, PR_NXT_INVALID, 0);
+				else { id[k] = my; len[k] = 0; }
+			}
+			any_live = any_live || id[k] != REC_INVALID;
+		}
+		if (__ballot_sync(0xffffffffu, !done || any_live) == 0) break;
+		if (row == ST_ROWS) {
+			if (chunk == ST_NONE && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);
+			const u32 c = __shfl_sync(0xffffffffu, nextc, 0);
+			if (c >= cap) { dev_fail(err, DE_STREAM_OVERFLOW); break; }
+			if (lane == 0) { if (chunk == ST_NONE) sp.chunk_head[wgid] = c; else sp.chunk_next[chunk] = c; }
+			chunk = c;
+			cp = c < sp.cap0 ? sp.base0 + (size_t)c * CHUNK : sp.base1 + (size_t)(c - sp.cap0) * CHUNK;
+			row = 0;
+		}
+		if (row == ST_ROWS - ST_AHEAD && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);
+		// all the gathers of this iteration go out before any of the symbol searches
+		i32 r[NS]; u32 vn[NS]; i32 bn[NS];
+		#pragma unroll
+		for (int k = 0; k < NS; k++) {
+			r[k] = (i32)(v[k] & LF_MASK); vn[k] = 0; bn[k] = 0;
+			if (id[k] != REC_INVALID && r[k] != idx) { bn[k] = row_to_byte(r[k], idx); vn[k] = ld_lf(lf + bn[k], pol_ld, false); }
+		}
+		#pragma unroll
+		for (int k = 0; k < NS; k++) {
+			if (id[k] != REC_INVALID) {
+				len[k]++;
+				bool stop = (r[k] == idx);
+				u32 nxt = S;
+				if (!stop) {
+					v[k] = vn[k];
+					if (vn[k] & LF_MARK) { stop = true; nxt = node_of(anchors, vn[k], r[k], bn[k], log2m, S); }
+				}
+				cp[row * ROW + k * 32 + lane] = (u8)symbol_of_row(sym, sh, r[k]);
+				if (stop) {
+					if (len[k] > PR_LEN_MAX) { dev_fail(err, DE_STREAM_OVERFLOW); len[k] = PR_LEN_MAX; }
+					rec[id[k]] = pack3(len[k], nxt, len[k]);
+					id[k] = REC_INVALID;
+				}
+			}
+		}
+		row++;
+	}
+}
+
+template __global__ void k_inv_walk_stream_ilp<4>(const u32* __restrict__, const InvMeta* __restrict__, i32, int, u32, u64* __restrict__, u32* __restrict__, u32* __restrict__, StreamSpace, int* __restrict__);
 
 } // namespace jp

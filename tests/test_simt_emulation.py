@@ -158,3 +158,28 @@ def test_emulated_suffix_array(emu, orc, kind, n, seed):
     b = T.tobytes()
     assert rc == 0
     assert sa.tolist() == sorted(range(n), key=lambda i: b[i:])
+
+
+@pytest.mark.parametrize("kind,n,seed", [("markov2", 65536 + 120, 3), ("repetitive", 150000, 3), ("alla", 70000, 0)])
+def test_emulated_single_walk_inverse_with_four_chains_per_thread(emu, orc, inv_env, kind, n, seed):
+    """JP_BWT_INV_ILP=4 (off by default): the *_ilp kernels -- four sub-chains per walker thread, stream rows of lane x slot."""
+    T = orc.gen(kind, n, seed)
+    B = orc.forward(T, "port")
+    inv_env["JP_BWT_INV_SINGLE"] = "1"
+    saved = os.environ.get("JP_BWT_INV_ILP")
+    os.environ["JP_BWT_INV_ILP"] = "4"
+    try:
+        for l2m in (None, "4"):
+            if l2m:
+                inv_env["JP_BWT_INV_LOG2M"] = l2m
+            for consume in (False, True):
+                rc, out, chunks, _ = emu.inverse(B, consume=consume)
+                assert rc == 0 and chunks > 0 and (out == T).all()
+        inv_env["JP_BWT_INV_STREAM_CAP"] = "2"
+        rc, out, chunks, launches = emu.inverse(B, consume=True)
+        assert rc == 0 and chunks < 0 and (out == T).all()
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_INV_ILP", None)
+        else:
+            os.environ["JP_BWT_INV_ILP"] = saved
