@@ -648,6 +648,53 @@ __global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, 
 	if (id > S && (nxt != id - 1 || dist != (u32)step)) dev_fail(err, DE_CHAIN_LEN);
 }
 
+// The same jumping with NR nodes per thread (ids id, id + stride, ...): the loop issues the NR record loads of a hop
+// together, so a thread has NR dependent chains of L2 accesses in flight instead of one (JP_BWT_INV_RANK_ILP=4; off by
+// default, to be measured -- the kernel above runs at 93 % occupancy and still uses 20 % of its issue slots).
+template <int NR>
+__global__ void __launch_bounds__(256) k_inv_rank_packed_ilp(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int hop_cap, u32 stride)
+{
+	const u32 nodes = S + N_ANCHOR;
+	const u32 id0 = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id0 >= stride || *(volatile int*)err != 0) return;
+	volatile u64* vrec = rec;
+	u32 len[NR], nxt[NR], dist[NR]; int hops[NR]; bool live[NR];
+	#pragma unroll
+	for (int k = 0; k < NR; k++) {
+		const u32 id = id0 + (u32)k * stride;
+		live[k] = false; len[k] = 0; nxt[k] = S; dist[k] = 0; hops[k] = 0;
+		if (id < nodes) {
+			const u64 r = vrec[id];
+			len[k] = pr_len(r); nxt[k] = pr_nxt(r); dist[k] = pr_dist(r);
+			live[k] = nxt[k] != PR_NXT_INVALID;
+		}
+	}
+	for (;;) {
+		u64 o[NR]; bool go[NR]; bool any = false;
+		#pragma unroll
+		for (int k = 0; k < NR; k++) { go[k] = live[k] && nxt[k] < S; o[k] = 0; if (go[k]) { o[k] = vrec[nxt[k]]; any = true; } }
+		if (!any) break;
+		#pragma unroll
+		for (int k = 0; k < NR; k++) {
+			if (!go[k]) continue;
+			const u32 id = id0 + (u32)k * stride;
+			const u32 onxt = pr_nxt(o[k]);
+			dist[k] += pr_dist(o[k]);
+			if (onxt == PR_NXT_INVALID || ++hops[k] > hop_cap) { dev_fail(err, DE_RANK_LOOP); nxt[k] = S; dist[k] = 0; continue; }
+			if (dist[k] > PR_DIST_MASK) { dev_fail(err, DE_CHAIN_LEN); nxt[k] = S; dist[k] = 0; continue; }
+			nxt[k] = onxt;
+			vrec[id] = pack3(len[k], nxt[k], dist[k]);
+		}
+	}
+	#pragma unroll
+	for (int k = 0; k < NR; k++) {
+		const u32 id = id0 + (u32)k * stride;
+		if (!live[k]) continue;
+		vrec[id] = pack3(len[k], nxt[k], dist[k]);
+		if (id > S && (nxt[k] != id - 1 || dist[k] != (u32)step)) dev_fail(err, DE_CHAIN_LEN);
+	}
+}
+
 // Zeroes the area the text is assembled in -- the head of the LF table -- unless the walk failed: the two-pass rerun
 // needs the table intact (in consume mode the BWT itself is gone by then).
 __global__ void __launch_bounds__(256) k_inv_clear_text(uint4* __restrict__ text, u32 n16, const int* __restrict__ err)
@@ -757,6 +804,12 @@ static int pick_log2m(i32 nlen)
 {
 	if (const char* e = getenv("JP_BWT_INV_LOG2M")) { int v = atoi(e); if (v >= 2 && v <= 12) return v; }
 	return nlen >= (1 << 22) ? 4 : 3;
+}
+
+static int rank_ilp()
+{
+	const char* e = getenv("JP_BWT_INV_RANK_ILP");
+	return (e && atoi(e) == 4) ? 4 : 1;
 }
 
 static int lf_blocks_per_sm()
@@ -935,7 +988,11 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
-		k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap); JP_LAUNCH(c);
+		if (rank_ilp() == 4) {
+			const u32 stride = (nodes + 3) / 4;
+			k_inv_rank_packed_ilp<4><<<(stride + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap, stride);
+		} else k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap);
+		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);

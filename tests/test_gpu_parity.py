@@ -583,7 +583,10 @@ def test_single_walk_inverse_with_four_chains_per_thread(jp, orc, single_walk_en
     B = jp.forward(T)
     single_walk_env["JP_BWT_INV_SINGLE"] = "1"
     saved = os.environ.get("JP_BWT_INV_ILP")
+    saved_rank = os.environ.get("JP_BWT_INV_RANK_ILP")
     os.environ["JP_BWT_INV_ILP"] = "4"
+    if seed % 2 == 0:
+        os.environ["JP_BWT_INV_RANK_ILP"] = "4"          # the queued ranking variant rides along on half of the cases
     try:
         out = jp.inverse(B)
         assert jp.last_stats().stream_chunks > 0
@@ -593,7 +596,8 @@ def test_single_walk_inverse_with_four_chains_per_thread(jp, orc, single_walk_en
             o = jp.inverse_device(d_in.clone(), consume=consume)
             assert jp.last_stats().stream_chunks > 0 and (o.cpu().numpy()[:n] == T).all()
     finally:
-        if saved is None:
-            os.environ.pop("JP_BWT_INV_ILP", None)
-        else:
-            os.environ["JP_BWT_INV_ILP"] = saved
+        for k, v in (("JP_BWT_INV_ILP", saved), ("JP_BWT_INV_RANK_ILP", saved_rank)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

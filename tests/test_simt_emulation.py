@@ -183,3 +183,30 @@ def test_emulated_single_walk_inverse_with_four_chains_per_thread(emu, orc, inv_
             os.environ.pop("JP_BWT_INV_ILP", None)
         else:
             os.environ["JP_BWT_INV_ILP"] = saved
+
+
+def test_emulated_ranking_with_four_nodes_per_thread(emu, orc, inv_env):
+    """JP_BWT_INV_RANK_ILP=4 (off by default): k_inv_rank_packed_ilp -- same records, four dependent chains per thread."""
+    saved = os.environ.get("JP_BWT_INV_RANK_ILP")
+    os.environ["JP_BWT_INV_RANK_ILP"] = "4"
+    inv_env["JP_BWT_INV_SINGLE"] = "1"
+    try:
+        for kind, n, seed in (("markov2", 65536 + 120, 3), ("repetitive", 150000, 3), ("alla", 70000, 0)):
+            T = orc.gen(kind, n, seed)
+            B = orc.forward(T, "port")
+            rc, out, chunks, _ = emu.inverse(B, consume=True)
+            assert rc == 0 and chunks > 0 and (out == T).all()
+        bad = B.copy()
+        bad[n + 4 * 50: n + 4 * 50 + 4] = np.frombuffer(np.int32(12345).tobytes(), dtype=np.uint8)
+        assert emu.inverse(bad)[0] == -6
+        rng = np.random.default_rng(2)
+        for _ in range(3):
+            bad = B.copy()
+            pos = rng.integers(0, n, 20)
+            bad[pos] = rng.integers(0, 256, 20).astype(np.uint8)
+            assert emu.inverse(bad)[0] in (0, -5, -6)
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_INV_RANK_ILP", None)
+        else:
+            os.environ["JP_BWT_INV_RANK_ILP"] = saved

@@ -1,6 +1,7 @@
 """Runs the A/B experiments that were built but not yet measured (they are all off by default):
   * JP_BWT_FWD_RUNSKIP=1   forward, single-symbol runs ordered by run length (bwt_forward.cu "run skip")
   * JP_BWT_INV_LF_BLOCKS=4 inverse LF build capped at 64 registers (4 blocks per SM)
+  * JP_BWT_INV_RANK_ILP=4  sub-chain ranking with four nodes per thread
   * JP_BWT_INV_ILP=4       single-walk inverse with four sub-chains per walker thread (a quarter of the warps)
 Each case runs in its own process (the switches are read per call, but a fresh process keeps the arenas comparable).
     python tools/queued_ab.py            # on a B200 box: prints one line per case, parity checked against golden hashes"""
@@ -31,6 +32,9 @@ if __name__ == "__main__":
     print("== inverse, LF build 3 / 4 blocks per SM")
     for v in ("3", "4"):
         run({"JP_BWT_INV_LF_BLOCKS": v}, "inv_ab.py", "markov2", "64")
+    print("== inverse, ranking 1 / 4 nodes per thread")
+    for v in ("1", "4"):
+        run({"JP_BWT_INV_RANK_ILP": v}, "inv_ab.py", "markov2", "64")
     print("== inverse one block at a time: one chain per lane (5 and 2 blocks of 8 warps per SM) / four chains per lane (1, 2, 3 blocks of 4 warps per SM)")
     for env in ({}, {"JP_BWT_INV_WBLOCKS_PER_SM": "2"}, {"JP_BWT_INV_ILP": "4", "JP_BWT_INV_WBLOCKS_PER_SM": "1"}, {"JP_BWT_INV_ILP": "4"},
                 {"JP_BWT_INV_ILP": "4", "JP_BWT_INV_WBLOCKS_PER_SM": "3"}):
