@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpbwt.so")
-SOURCES = ["jp_bwt_api.cu", "bwt_inverse.cu", "bwt_inverse_ilp.cu", "bwt_forward.cu"]
+SOURCES = ["jp_bwt_api.cu", "bwt_inverse.cu", "bwt_forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--use_fast_math", "-DRS_SCATTER_MIN_BLOCKS=3"]
 

@@ -163,10 +163,9 @@ __global__ void __launch_bounds__(256) k_inv_ctable(const u32* __restrict__ bin_
 // coalesced 128 B rows of 32-bit words and re-distributed by shuffle so that lane l handles byte
 // 32*k + l of the row (text order == lane order). Equal bytes inside a warp step are ranked with
 // match.any; running per-warp counters live in shared memory; LF values leave as 128 B coalesced rows.
-// MINB = resident blocks per SM asked of the compiler: 3 (80 registers) is the measured configuration; 4 caps the
-// kernel at 64 registers with 16 bytes of spill -- JP_BWT_INV_LF_BLOCKS=4 selects it, to be measured.
-template <int MINB>
-__global__ void __launch_bounds__(INV_THREADS, MINB) k_inv_lf(const u8* __restrict__ bwt, i32 n,
+// 4 resident blocks per SM asked of the compiler: that caps the kernel at 64 registers with 16 bytes of spill and was
+// measured at 0.185 ms per 64 MiB block against 0.222 ms for the 80-register / 3-block build (profiles/ab_r02.md).
+__global__ void __launch_bounds__(INV_THREADS, 4) k_inv_lf(const u8* __restrict__ bwt, i32 n,
                                                         const u32* __restrict__ tile_excl, const InvMeta* __restrict__ meta,
                                                         u32* __restrict__ lf, int log2m)
 {
@@ -648,53 +647,6 @@ __global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, 
 	if (id > S && (nxt != id - 1 || dist != (u32)step)) dev_fail(err, DE_CHAIN_LEN);
 }
 
-// The same jumping with NR nodes per thread (ids id, id + stride, ...): the loop issues the NR record loads of a hop
-// together, so a thread has NR dependent chains of L2 accesses in flight instead of one (JP_BWT_INV_RANK_ILP=4; off by
-// default, to be measured -- the kernel above runs at 93 % occupancy and still uses 20 % of its issue slots).
-template <int NR>
-__global__ void __launch_bounds__(256) k_inv_rank_packed_ilp(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int hop_cap, u32 stride)
-{
-	const u32 nodes = S + N_ANCHOR;
-	const u32 id0 = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id0 >= stride || *(volatile int*)err != 0) return;
-	volatile u64* vrec = rec;
-	u32 len[NR], nxt[NR], dist[NR]; int hops[NR]; bool live[NR];
-	#pragma unroll
-	for (int k = 0; k < NR; k++) {
-		const u32 id = id0 + (u32)k * stride;
-		live[k] = false; len[k] = 0; nxt[k] = S; dist[k] = 0; hops[k] = 0;
-		if (id < nodes) {
-			const u64 r = vrec[id];
-			len[k] = pr_len(r); nxt[k] = pr_nxt(r); dist[k] = pr_dist(r);
-			live[k] = nxt[k] != PR_NXT_INVALID;
-		}
-	}
-	for (;;) {
-		u64 o[NR]; bool go[NR]; bool any = false;
-		#pragma unroll
-		for (int k = 0; k < NR; k++) { go[k] = live[k] && nxt[k] < S; o[k] = 0; if (go[k]) { o[k] = vrec[nxt[k]]; any = true; } }
-		if (!any) break;
-		#pragma unroll
-		for (int k = 0; k < NR; k++) {
-			if (!go[k]) continue;
-			const u32 id = id0 + (u32)k * stride;
-			const u32 onxt = pr_nxt(o[k]);
-			dist[k] += pr_dist(o[k]);
-			if (onxt == PR_NXT_INVALID || ++hops[k] > hop_cap) { dev_fail(err, DE_RANK_LOOP); nxt[k] = S; dist[k] = 0; continue; }
-			if (dist[k] > PR_DIST_MASK) { dev_fail(err, DE_CHAIN_LEN); nxt[k] = S; dist[k] = 0; continue; }
-			nxt[k] = onxt;
-			vrec[id] = pack3(len[k], nxt[k], dist[k]);
-		}
-	}
-	#pragma unroll
-	for (int k = 0; k < NR; k++) {
-		const u32 id = id0 + (u32)k * stride;
-		if (!live[k]) continue;
-		vrec[id] = pack3(len[k], nxt[k], dist[k]);
-		if (id > S && (nxt[k] != id - 1 || dist[k] != (u32)step)) dev_fail(err, DE_CHAIN_LEN);
-	}
-}
-
 // Zeroes the area the text is assembled in -- the head of the LF table -- unless the walk failed: the two-pass rerun
 // needs the table intact (in consume mode the BWT itself is gone by then).
 __global__ void __launch_bounds__(256) k_inv_clear_text(uint4* __restrict__ text, u32 n16, const int* __restrict__ err)
@@ -786,16 +738,6 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 
 	}
 }
 
-// ---- single-walk path, several sub-chains per walker thread: declarations (the kernels are at the end of the file) ----
-constexpr int ILP_THREADS = 128;
-constexpr int ILP_WARPS   = ILP_THREADS / 32;
-template <int NS>
-__global__ void k_inv_walk_stream_ilp(const u32* __restrict__ lf, const InvMeta* __restrict__ meta, i32 n, int log2m, u32 S, u64* __restrict__ rec,
-                                      u32* __restrict__ ticket, u32* __restrict__ chunk_ctr, StreamSpace sp, int* __restrict__ err);
-// the replay kernel of this variant lives in bwt_inverse_ilp.cu (a second copy of the replay loop in this translation unit
-// changes the schedule nvcc picks for k_inv_place; the measured kernels are to stay bit-identical)
-void launch_inv_place_ilp4(int blocks, cudaStream_t s, i32 n, i32 step, u32 S, const u64* rec, StreamSpace sp, u8* out, int* err);
-
 // ---- host driver -----------------------------------------------------------------------------------
 // Marker spacing m. A pass costs about nlen / (gather rate) + (longest sub-chain) * (unloaded DRAM latency), and
 // the longest of nlen/m geometric sub-chains is ~ m * ln(nlen/m): measured on 64 MiB, m = 64 / 32 / 16 give
@@ -804,18 +746,6 @@ static int pick_log2m(i32 nlen)
 {
 	if (const char* e = getenv("JP_BWT_INV_LOG2M")) { int v = atoi(e); if (v >= 2 && v <= 12) return v; }
 	return nlen >= (1 << 22) ? 4 : 3;
-}
-
-static int rank_ilp()
-{
-	const char* e = getenv("JP_BWT_INV_RANK_ILP");
-	return (e && atoi(e) == 4) ? 4 : 1;
-}
-
-static int lf_blocks_per_sm()
-{
-	const char* e = getenv("JP_BWT_INV_LF_BLOCKS");
-	return (e && atoi(e) == 4) ? 4 : 3;
 }
 
 static int walk_flags()
@@ -835,7 +765,6 @@ struct InvBuffers {
 	u32* lf; u32* tile_hist; u32* bin_total; InvMeta* meta; u64* rec; u32* ticket; int* err;
 	int tiles; int log2m; u32 S;
 	bool single;                  // single-walk path (k_inv_walk_stream / k_inv_place)
-	int  ilp;                     // sub-chains per walker thread: 1, or 4 (JP_BWT_INV_ILP=4: the *_ilp kernels, ILP_THREADS wide)
 	int  wblocks;                 // walker blocks of the single-walk kernels (the replay needs the same grid)
 	StreamSpace sp;
 };
@@ -867,22 +796,8 @@ static int inv_alloc(Ctx& c, i32 nlen, InvBuffers& b, u8* scratch_in = nullptr, 
 	size_t extra_stream = 0, in_free_off = 0, in_free = 0;
 	b.wblocks = 0;
 	b.sp = StreamSpace{};
-	b.ilp = 1;
-	if (const char* e = getenv("JP_BWT_INV_ILP")) if (atoi(e) == 4) b.ilp = 4;
-	const size_t chunk_bytes = (size_t)ST_CHUNK * b.ilp;            // 32 rows of 32 * ilp bytes
-	const int wthreads = b.ilp > 1 ? ILP_THREADS : INV_THREADS;
-	if (b.single && b.ilp > 1) {
-		int per_sm = 2;                                               // 2 x 4 warps x 32 lanes x 4 sub-chains = 1024 gathers in flight per SM
-		if (const char* e = getenv("JP_BWT_INV_WBLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
-		b.wblocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)per_sm * c.sm_count, nodes / ((size_t)wthreads * b.ilp * 8)));
-		if (rec_in_input) {
-			in_free_off = (nodes * 8 + 15) & ~(size_t)15;
-			in_free = (size_t)nlen > in_free_off ? (size_t)nlen - in_free_off : 0;
-		} else extra_stream = (size_t)nlen / 2;
-		if (mode == 1) extra_stream += (size_t)nlen / 2 + (size_t)b.wblocks * (wthreads / 32) * 160 * 32 * b.ilp;
-		b.sp.cap0 = (u32)((size_t)nlen / chunk_bytes);
-		b.sp.batch_cap = (u32)(nodes / WALK_BATCH + (size_t)b.wblocks * (wthreads / 32) * 4 * b.ilp + 16);
-	} else
+	const size_t chunk_bytes = (size_t)ST_CHUNK;
+	const int wthreads = INV_THREADS;
 	if (b.single) {
 		// every lane should see a handful of sub-chains, or the tail rows dominate the stream
 		// (measured on 64 MiB: 8 / 6 / 5 / 4 / 3 blocks per SM walk in 1.154 / 1.142 / 1.146 / 1.173 / 1.388 ms and leave
@@ -966,8 +881,7 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 	JP_TRY(inv_alloc(c, nlen, b, scratch_in, d_out));
 	JP_TRY(inv_build_table(c, d_in, len, nlen, d_out, b, s));
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
-	if (lf_blocks_per_sm() == 4) k_inv_lf<4><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m);
-	else k_inv_lf<3><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m);
+	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m);
 	JP_LAUNCH(c);
 	k_inv_mark_anchors<<<1, 128, 0, s>>>(b.meta, b.lf, nlen); JP_LAUNCH(c);
 	JP_KCHECK();
@@ -983,21 +897,16 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		// (serialising the walks of the blocks in flight on one GPU behind a host-side gate, so that the other blocks'
 		// table builds, rankings and placements could fill in beside a single DRAM-bound walk, was measured: 35.3-35.6
 		// against 35.7-36.0 GB/s with four blocks in flight -- the hardware's own interleaving is as good)
-		if (b.ilp == 4) k_inv_walk_stream_ilp<4><<<b.wblocks, ILP_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
-		else k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
+		k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
-		if (rank_ilp() == 4) {
-			const u32 stride = (nodes + 3) / 4;
-			k_inv_rank_packed_ilp<4><<<(stride + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap, stride);
-		} else k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap);
+		k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap);
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);
-		if (b.ilp == 4) launch_inv_place_ilp4(b.wblocks, s, nlen, step, b.S, b.rec, b.sp, text, b.err);
-		else k_inv_place<<<b.wblocks, INV_THREADS, 0, s>>>(nlen, step, b.S, b.rec, b.sp, text, b.err);
+		k_inv_place<<<b.wblocks, INV_THREADS, 0, s>>>(nlen, step, b.S, b.rec, b.sp, text, b.err);
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaMemcpyAsync(d_out, text, (size_t)nlen, cudaMemcpyDeviceToDevice, s));   // (meaningless but harmless after a failure)
@@ -1005,7 +914,7 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		JP_CUDA(cudaMemcpyAsync(c.h_small, b.err, sizeof(int), cudaMemcpyDeviceToHost, s));
 		JP_CUDA(cudaMemcpyAsync(c.h_small + 4, b.ticket + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));
 		JP_CUDA(cudaStreamSynchronize(s));
-		st->stream_chunks = (i32)std::min<u64>((u64)(u32)c.h_small[4] * (u64)b.ilp, 0x7fffffffull);   // in KiB whatever the chunk size
+		st->stream_chunks = (i32)std::min<u64>((u64)(u32)c.h_small[4], 0x7fffffffull);   // 1 KiB chunks
 		st->random_sectors = (u64)nlen;
 		if (c.h_small[0] == DE_STREAM_OVERFLOW) {                           // rare: rerun on the intact LF table
 			two_pass = true;
@@ -1070,7 +979,7 @@ int debug_lf(Ctx& c, const u8* h_in, i32 nlen, i32* h_lf, i32* h_ctable)
 		JP_CUDA(cudaStreamSynchronize(s));
 	}
 	JP_TRY(inv_build_table(c, d_in, nlen, nlen, d_out, b, s));
-	k_inv_lf<3><<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
+	k_inv_lf<<<b.tiles, INV_THREADS, 0, s>>>(d_in, nlen, b.tile_hist, b.meta, b.lf, b.log2m); JP_LAUNCH(c);
 	k_strip_marks<<<(nlen + 255) / 256, 256, 0, s>>>(b.lf, nlen); JP_LAUNCH(c);
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(h_lf, b.lf, (size_t)nlen * 4, cudaMemcpyDeviceToHost, s));
@@ -1129,96 +1038,5 @@ double debug_gather_rate(Ctx& c, u64 table_bytes, i32 chains, i32 steps, int dep
 	}
 	return (double)blocks * 256.0 * (double)steps / ((double)best * 1e-3);
 }
-
-// ---- single-walk path, several sub-chains per walker thread (JP_BWT_INV_ILP=4; off by default, to be measured) ----
-// Same algorithm, different shape: every lane interleaves NS sub-chains, so a warp keeps 32 * NS gathers in flight and
-// a walk saturates DRAM from a quarter of the warps (and of the registers) the one-chain-per-lane kernel holds for its
-// whole duration -- room in which the issue-bound kernels of OTHER blocks in flight can run beside it.
-// A stream row is now lane x slot (NS * 32 bytes, slot-major), a chunk 32 rows; tickets are drawn slot by slot, which
-// the replay repeats literally. Blocks are ILP_THREADS wide in both kernels (the replay stages a whole chunk per warp).
-
-template <int NS>
-__global__ void __launch_bounds__(ILP_THREADS) k_inv_walk_stream_ilp(const u32* __restrict__ lf, const InvMeta* __restrict__ meta,
-                                                                     i32 n, int log2m, u32 S, u64* __restrict__ rec,
-                                                                     u32* __restrict__ ticket, u32* __restrict__ chunk_ctr,
-                                                                     StreamSpace sp, int* __restrict__ err)
-{
-	constexpr u32 ROW = 32u * NS, CHUNK = ST_ROWS * ROW;
-	__shared__ AnchorTable anchors;
-	__shared__ SymTable sym;
-	const int sh = sym_shift(n);
-	load_anchor_table(anchors, meta);
-	load_sym_table(sym, meta, sh);
-	const i32 idx = meta->idx;
-	const u32 nodes = S + N_ANCHOR;
-	const u32 lane = lane_id();
-	const u32 wgid = blockIdx.x * ILP_WARPS + (threadIdx.x >> 5);
-	const u32 cap = sp.cap0 + sp.cap1;
-	const u64 pol_ld = policy_evict_first();
-	WarpTickets wt = {0, 0};
-	u32 id[NS], v[NS], len[NS];
-	#pragma unroll
-	for (int k = 0; k < NS; k++) { id[k] = REC_INVALID; v[k] = 0; len[k] = 0; }
-	u32 prev_batch = ST_NONE, chunk = ST_NONE, nextc = 0, row = ST_ROWS;
-	u8* cp = nullptr;
-	bool done = false;
-	for (;;) {
-		bool any_live = false;
-		#pragma unroll
-		for (int k = 0; k < NS; k++) {
-			const u32 my = take_ticket_log(wt, !done && id[k] == REC_INVALID, ticket, nodes, done, prev_batch, wgid, sp, err);
-			if (my != REC_INVALID) {
-				const i32 bi = node_start(my, S, n, log2m, meta, idx);
-				bool live = bi >= 0;
-				if (live) {
-					v[k] = ld_lf(lf + bi, pol_ld, false);
-					live = my >= S || (v[k] & LF_ANCHOR) == 0;
-				}
-				if (!live) rec[my] = pack3(0, PR_NXT_INVALID, 0);
-				else { id[k] = my; len[k] = 0; }
-			}
-			any_live = any_live || id[k] != REC_INVALID;
-		}
-		if (__ballot_sync(0xffffffffu, !done || any_live) == 0) break;
-		if (row == ST_ROWS) {
-			if (chunk == ST_NONE && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);
-			const u32 c = __shfl_sync(0xffffffffu, nextc, 0);
-			if (c >= cap) { dev_fail(err, DE_STREAM_OVERFLOW); break; }
-			if (lane == 0) { if (chunk == ST_NONE) sp.chunk_head[wgid] = c; else sp.chunk_next[chunk] = c; }
-			chunk = c;
-			cp = c < sp.cap0 ? sp.base0 + (size_t)c * CHUNK : sp.base1 + (size_t)(c - sp.cap0) * CHUNK;
-			row = 0;
-		}
-		if (row == ST_ROWS - ST_AHEAD && lane == 0) nextc = atomicAdd(chunk_ctr, 1u);
-		// all the gathers of this iteration go out before any of the symbol searches
-		i32 r[NS]; u32 vn[NS]; i32 bn[NS];
-		#pragma unroll
-		for (int k = 0; k < NS; k++) {
-			r[k] = (i32)(v[k] & LF_MASK); vn[k] = 0; bn[k] = 0;
-			if (id[k] != REC_INVALID && r[k] != idx) { bn[k] = row_to_byte(r[k], idx); vn[k] = ld_lf(lf + bn[k], pol_ld, false); }
-		}
-		#pragma unroll
-		for (int k = 0; k < NS; k++) {
-			if (id[k] != REC_INVALID) {
-				len[k]++;
-				bool stop = (r[k] == idx);
-				u32 nxt = S;
-				if (!stop) {
-					v[k] = vn[k];
-					if (vn[k] & LF_MARK) { stop = true; nxt = node_of(anchors, vn[k], r[k], bn[k], log2m, S); }
-				}
-				cp[row * ROW + k * 32 + lane] = (u8)symbol_of_row(sym, sh, r[k]);
-				if (stop) {
-					if (len[k] > PR_LEN_MAX) { dev_fail(err, DE_STREAM_OVERFLOW); len[k] = PR_LEN_MAX; }
-					rec[id[k]] = pack3(len[k], nxt, len[k]);
-					id[k] = REC_INVALID;
-				}
-			}
-		}
-		row++;
-	}
-}
-
-template __global__ void k_inv_walk_stream_ilp<4>(const u32* __restrict__, const InvMeta* __restrict__, i32, int, u32, u64* __restrict__, u32* __restrict__, u32* __restrict__, StreamSpace, int* __restrict__);
 
 } // namespace jp

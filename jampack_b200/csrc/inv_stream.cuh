@@ -1,5 +1,5 @@
-// inv_stream.cuh -- stream layout and packed sub-chain records of the single-walk inverse, shared by bwt_inverse.cu and
-// bwt_inverse_ilp.cu. Included INSIDE namespace jp (it opens none), after common.cuh.
+// inv_stream.cuh -- stream layout and packed sub-chain records of the single-walk inverse, used by bwt_inverse.cu.
+// Included INSIDE namespace jp (it opens none), after common.cuh.
 #pragma once
 constexpr u32 INV_REC_INVALID = 0xffffffffu;
 constexpr u32 INV_WALK_BATCH  = 128;

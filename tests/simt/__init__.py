@@ -28,9 +28,9 @@ def build(force=False):
     if not force and not _stale():
         return LIB
     from . import gen
-    gen.main(["common.cuh", "bwt_internal.cuh", "radix_sort.cuh", "inv_stream.cuh", "bwt_inverse.cu", "bwt_inverse_ilp.cu", "bwt_forward.cu"])
+    gen.main(["common.cuh", "bwt_internal.cuh", "radix_sort.cuh", "inv_stream.cuh", "bwt_inverse.cu", "bwt_forward.cu"])
     cmd = ["g++", "-std=c++17", "-O1", "-w", "-fPIC", "-shared", "-I", HERE, "-I", OUT, "-o", LIB,
-           os.path.join(OUT, "bwt_inverse.cpp"), os.path.join(OUT, "bwt_inverse_ilp.cpp"), os.path.join(OUT, "bwt_forward.cpp"),
+           os.path.join(OUT, "bwt_inverse.cpp"), os.path.join(OUT, "bwt_forward.cpp"),
            os.path.join(HERE, "harness.cpp"), os.path.join(HERE, "simt_runtime.cpp")]
     env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
     subprocess.run(cmd, check=True, env=env)

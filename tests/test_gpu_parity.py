@@ -569,35 +569,3 @@ def test_forward_run_skip_is_bit_exact(jp, orc, kind, n, seed):
     assert (got == want).all()
     if kind == "alla" and n >= MiB:
         assert rounds <= 2
-
-
-@pytest.mark.skipif(os.environ.get("JP_BWT_TEST_EXPERIMENTAL") != "1",
-                    reason="JP_BWT_INV_ILP=4 is off by default and has only been verified under SIMT emulation so far; "
-                           "set JP_BWT_TEST_EXPERIMENTAL=1 to run it on the GPU")
-@pytest.mark.parametrize("kind,n,seed", [("markov2", 65536 + 120, 3), ("uniform", MiB, 2), ("repetitive", 2 * MiB + 5, 3),
-                                         ("alla", MiB + 120, 0), ("markov2", 40 * MiB + 77, 4)])
-def test_single_walk_inverse_with_four_chains_per_thread(jp, orc, single_walk_env, kind, n, seed):
-    """JP_BWT_INV_ILP=4: the *_ilp kernels (four sub-chains per walker thread) give the same bytes."""
-    import torch
-    T = orc.gen(kind, n, seed)
-    B = jp.forward(T)
-    single_walk_env["JP_BWT_INV_SINGLE"] = "1"
-    saved = os.environ.get("JP_BWT_INV_ILP")
-    saved_rank = os.environ.get("JP_BWT_INV_RANK_ILP")
-    os.environ["JP_BWT_INV_ILP"] = "4"
-    if seed % 2 == 0:
-        os.environ["JP_BWT_INV_RANK_ILP"] = "4"          # the queued ranking variant rides along on half of the cases
-    try:
-        out = jp.inverse(B)
-        assert jp.last_stats().stream_chunks > 0
-        assert (out == T).all()
-        d_in = torch.from_numpy(B.copy()).cuda()
-        for consume in (False, True):
-            o = jp.inverse_device(d_in.clone(), consume=consume)
-            assert jp.last_stats().stream_chunks > 0 and (o.cpu().numpy()[:n] == T).all()
-    finally:
-        for k, v in (("JP_BWT_INV_ILP", saved), ("JP_BWT_INV_RANK_ILP", saved_rank)):
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v

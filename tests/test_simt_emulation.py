@@ -160,53 +160,3 @@ def test_emulated_suffix_array(emu, orc, kind, n, seed):
     assert sa.tolist() == sorted(range(n), key=lambda i: b[i:])
 
 
-@pytest.mark.parametrize("kind,n,seed", [("markov2", 65536 + 120, 3), ("repetitive", 150000, 3), ("alla", 70000, 0)])
-def test_emulated_single_walk_inverse_with_four_chains_per_thread(emu, orc, inv_env, kind, n, seed):
-    """JP_BWT_INV_ILP=4 (off by default): the *_ilp kernels -- four sub-chains per walker thread, stream rows of lane x slot."""
-    T = orc.gen(kind, n, seed)
-    B = orc.forward(T, "port")
-    inv_env["JP_BWT_INV_SINGLE"] = "1"
-    saved = os.environ.get("JP_BWT_INV_ILP")
-    os.environ["JP_BWT_INV_ILP"] = "4"
-    try:
-        for l2m in (None, "4"):
-            if l2m:
-                inv_env["JP_BWT_INV_LOG2M"] = l2m
-            for consume in (False, True):
-                rc, out, chunks, _ = emu.inverse(B, consume=consume)
-                assert rc == 0 and chunks > 0 and (out == T).all()
-        inv_env["JP_BWT_INV_STREAM_CAP"] = "2"
-        rc, out, chunks, launches = emu.inverse(B, consume=True)
-        assert rc == 0 and chunks < 0 and (out == T).all()
-    finally:
-        if saved is None:
-            os.environ.pop("JP_BWT_INV_ILP", None)
-        else:
-            os.environ["JP_BWT_INV_ILP"] = saved
-
-
-def test_emulated_ranking_with_four_nodes_per_thread(emu, orc, inv_env):
-    """JP_BWT_INV_RANK_ILP=4 (off by default): k_inv_rank_packed_ilp -- same records, four dependent chains per thread."""
-    saved = os.environ.get("JP_BWT_INV_RANK_ILP")
-    os.environ["JP_BWT_INV_RANK_ILP"] = "4"
-    inv_env["JP_BWT_INV_SINGLE"] = "1"
-    try:
-        for kind, n, seed in (("markov2", 65536 + 120, 3), ("repetitive", 150000, 3), ("alla", 70000, 0)):
-            T = orc.gen(kind, n, seed)
-            B = orc.forward(T, "port")
-            rc, out, chunks, _ = emu.inverse(B, consume=True)
-            assert rc == 0 and chunks > 0 and (out == T).all()
-        bad = B.copy()
-        bad[n + 4 * 50: n + 4 * 50 + 4] = np.frombuffer(np.int32(12345).tobytes(), dtype=np.uint8)
-        assert emu.inverse(bad)[0] == -6
-        rng = np.random.default_rng(2)
-        for _ in range(3):
-            bad = B.copy()
-            pos = rng.integers(0, n, 20)
-            bad[pos] = rng.integers(0, 256, 20).astype(np.uint8)
-            assert emu.inverse(bad)[0] in (0, -5, -6)
-    finally:
-        if saved is None:
-            os.environ.pop("JP_BWT_INV_RANK_ILP", None)
-        else:
-            os.environ["JP_BWT_INV_RANK_ILP"] = saved
