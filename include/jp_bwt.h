@@ -110,12 +110,18 @@ typedef struct jp_bwt_stats {
 	uint64_t random_sectors;     /* counted 32 B random sector touches (SURVEY.md 8d model)            */
 	float    ms_total;           /* device time of the whole call (CUDA events)                        */
 	float    ms_h2d, ms_d2h;     /* host entry points only                                             */
-	float    ms_phase[8];        /* forward: 0 keys 1 initial sort 2 initial ranks 3 rounds 4 emit      */
+	float    ms_phase[8];        /* forward: 0 setup + keys 1 initial sort 2 initial ranks 3 rounds 4 emit */
 	                             /* inverse: 0 prepare+histogram 1 LF build 2 length walk 3 ranking 4 emit walk */
 	                             /*          (single-walk path: 2 decode walk 3 ranking 4 placement + copy)     */
 	float    active_fraction[JP_BWT_MAX_ROUNDS]; /* forward: a_r = suffixes still unsorted entering round r */
 	int32_t  stream_chunks;      /* inverse: 1 KiB stream chunks the single-walk path used; 0 = two-pass path,  */
 	                             /* negative = the stream space overflowed and the two-pass path was rerun      */
+	float    large_fraction;     /* forward: share of the block that went through the large-group route, summed */
+	                             /* over the rounds                                                              */
+	int32_t  radix_tiles;        /* forward: tiles that took the shared-memory radix route, summed over rounds   */
+	int32_t  bypass_suffixes;    /* forward: suffixes inside single-symbol runs, placed without sorting          */
+	int32_t  bypass_runs;        /* forward: the runs they belong to                                              */
+	int32_t  period;             /* forward: period of the repeats ordered by length instead of by doubling; 0 = none */
 } jp_bwt_stats;
 
 /* Stats of the last call made by the calling thread. */

@@ -36,7 +36,9 @@ class Stats(C.Structure):
                 ("initial_depth", C.c_int32), ("subchains", C.c_int32), ("subchain_spacing", C.c_int32),
                 ("device_bytes", C.c_uint64), ("random_sectors", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_phase", C.c_float * 8), ("active_fraction", C.c_float * MAX_ROUNDS), ("stream_chunks", C.c_int32)]
+                ("ms_phase", C.c_float * 8), ("active_fraction", C.c_float * MAX_ROUNDS), ("stream_chunks", C.c_int32),
+                ("large_fraction", C.c_float), ("radix_tiles", C.c_int32), ("bypass_suffixes", C.c_int32),
+                ("bypass_runs", C.c_int32), ("period", C.c_int32)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_phase", "active_fraction")}
@@ -186,8 +188,10 @@ def inverse_device(d_in, d_out=None, consume=False):
     import torch
     assert d_in.is_cuda and d_in.dtype == torch.uint8 and d_in.is_contiguous()
     n = d_in.numel()
+    assert n >= TRAILER, "an inverse input carries the 480-byte trailer"
     if d_out is None:
         d_out = torch.zeros(max(n - TRAILER, 1), dtype=torch.uint8, device=d_in.device)
+    assert d_out.is_cuda and d_out.dtype == torch.uint8 and d_out.is_contiguous() and d_out.numel() >= n - TRAILER
     fn = lib().jp_bwt_inverse_device_consume if consume else lib().jp_bwt_inverse_device
     _check(fn(d_in.data_ptr(), n, d_out.data_ptr(), d_in.device.index or 0, _stream_of(d_in)), "jp_bwt_inverse_device")
     return d_out

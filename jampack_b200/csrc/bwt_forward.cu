@@ -4,51 +4,70 @@
 // (divsufsort.cpp:1721; contract divsufsort.hpp:37-45: plain suffix array, a proper prefix sorts first).
 // Nothing of divsufsort's induced-copying design is kept: a serial induce pass has no place on 148 SMs.
 //
-//   1. symbol remap   present byte values -> dense codes 1..sigma (0 = end of string), b = ceil(log2(sigma+1)) bits
-//   2. initial keys   key(i) = the first d = floor(64/b) codes of suffix i, zero padded: the padding IS the
-//                     sentinel, so "shorter sorts first" needs no tie-break and no suffix shorter than the
-//                     current depth is ever in a group with another one
+//   1. symbol remap   present byte values -> dense codes 1..sigma (0 = end of string)
+//   2. initial keys   key(i) = the first d codes of suffix i as a base-(sigma+1) number, zero padded: the padding IS
+//                     the sentinel, so "shorter sorts first" needs no tie-break
 //   3. radix bucket   LSD radix sort of (key, i)                                      [radix_sort.cuh]
-//   4. ranks          group heads = key changes; rank = 1 + position of the group's head; singletons retire
-//                     into SA at once, the rest are compacted into the active set
-//   5. doubling       while any group is unsorted: key = (dense group id, ISA[s + h]) -> radix sort ->
-//                     heads/ranks/retire/compact; h doubles. Only the active set is touched (Larsson-Sadakane
-//                     discarding); ISA[nlen] = 0 is the empty suffix.
+//   4. ranks          the sorted suffix ids ARE the suffix array, in place; group heads = key changes; rank = 1 +
+//                     position of the group's head; singletons are final, the rest form the ACTIVE SET: one 32-bit
+//                     word per unsorted suffix = its SA position, bit 31 = first of its group
+//   5. doubling       while any group is unsorted: every active suffix s takes key2 = ISA[s + h]; groups are refined in
+//                     place in SA by key2 (shared-memory kernels for groups up to a tile, a global radix sort for longer
+//                     ones), ranks are updated, sorted suffixes leave the active set; h doubles. Only the active set is
+//                     touched (Larsson-Sadakane discarding); ISA[nlen] = 0 is the empty suffix.
 //   6. emit           bwt[o] = T[SA[row]-1] with the row of suffix 0 skipped (bwt.cpp:50-56), the sampled
 //                     indices ISA[k*step] (bwt.cpp:44-48,57-61), the raw tail (bwt.cpp:32-33).
+//
+// Device memory: six units of 4(N+2) bytes -- two (key, id) buffer pairs during the initial sort; SA, ISA, two
+// active-set buffers, a staging unit and a spare during the rounds -- plus N/4 of radix histograms: 24.3 N. The
+// one-byte arrays (next-digit bytes of the radix passes, head flags of the rounds) live in the caller's output block,
+// which is dead until the emission.
 #include "bwt_internal.cuh"
 #include "radix_sort.cuh"
+#include <algorithm>
 #include <chrono>
 
 namespace jp {
+
+constexpr u32 AP_HEAD = 0x80000000u;     // active-set word: this slot is the first of its group
+constexpr u32 AP_POS  = 0x3fffffffu;     // ... and its position in SA (blocks stay below 2^30, bwt_internal.cuh)
 
 struct FwdMeta {
 	u32 code[256];
 	i32 sigma, bits, depth, key_bits;   // bits: per symbol (reported); depth: symbols per key; key_bits: bit length of the largest key
 	u32 hist[256];
+	u32 eq4;                            // aligned 4-byte words of one repeated byte: a cheap screen for single-symbol runs
 };
 
 // ---- 1. symbol histogram and dense codes -------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fwd_symhist(const u8* __restrict__ T, i32 n, FwdMeta* __restrict__ meta)
 {
 	__shared__ u32 h[8][256];
+	__shared__ u32 s_eq4;
 	const int t = threadIdx.x, w = t >> 5;
 	for (int i = t; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+	if (t == 0) s_eq4 = 0;
 	__syncthreads();
 	const i64 stride = (i64)gridDim.x * 256 * 16;
+	u32 eq4 = 0;
 	for (i64 p = ((i64)blockIdx.x * 256 + t) * 16; p < n; p += stride) {
 		if (p + 16 <= n) {
 			const uint4 q = __ldg(reinterpret_cast<const uint4*>(T + p));
 			const u32 wd[4] = {q.x, q.y, q.z, q.w};
 			#pragma unroll
+			for (int k = 0; k < 4; k++) eq4 += (wd[k] == (wd[k] & 255u) * 0x01010101u);
+			#pragma unroll
 			for (int k = 0; k < 16; k++) atomicAdd(&h[w][(wd[k >> 2] >> ((k & 3) * 8)) & 255], 1u);
 		} else for (i64 q = p; q < n; q++) atomicAdd(&h[w][T[q]], 1u);
 	}
+	eq4 = warp_sum(eq4);
+	if ((t & 31) == 0 && eq4) atomicAdd(&s_eq4, eq4);
 	__syncthreads();
 	u32 s = 0;
 	#pragma unroll
 	for (int k = 0; k < 8; k++) s += h[k][t];
 	if (s) atomicAdd(&meta->hist[t], s);
+	if (t == 0 && s_eq4) atomicAdd(&meta->eq4, s_eq4);
 }
 
 __global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
@@ -128,32 +147,33 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 	tile_hist[(size_t)t * stride + blockIdx.x] = sum;
 }
 
-// ---- 4/5. group heads -> ranks, retire singletons, compact the rest ----------------------------------
-// Scan element: (P of the last group head so far, #survivors, #surviving group heads).
+// ---- 4. group heads -> ranks, retire singletons, compact the rest -------------------------------------
+// The suffix array is refined IN PLACE: a slot of the active set names a position of SA, positions of a group are
+// consecutive, and a suffix that has become a singleton simply stays where it is. What the grouping step produces per
+// slot is (a) the rank of its suffix = 1 + position of the group's head and (b), for slots of groups that are still
+// unsorted, the next active set. Scan element: (position of the last group head so far, #survivors, #surviving heads).
 constexpr int GS_THREADS = 256;
 constexpr int GS_SUB     = 8;
 constexpr int GS_TILE    = GS_THREADS * GS_SUB;
 struct GAgg { i32 mh; u32 ns; u32 ng; u32 pad; };
 
-// Group boundaries come either from the sorted keys (a key change) or, after the shared-memory segmented sort,
-// from the one-byte head flags it wrote.
-struct GFlags { bool head, nhead; };
-__device__ __forceinline__ GFlags group_flags(const u64* __restrict__ K, const u8* __restrict__ F, u32 j, u32 A)
+// head flags of the initial order: a key change
+__global__ void __launch_bounds__(256) k_fwd_flags(const u64* __restrict__ K, u32 n, u8* __restrict__ F)
 {
-	GFlags f;
-	if (F) {
-		f.head = F[j] != 0;
-		f.nhead = (j + 1 == A) || (F[j + 1] != 0);
-	} else {
-		const u64 kj = K[j];
-		f.head = (j == 0) || (K[j - 1] != kj);
-		f.nhead = (j + 1 == A) || (K[j + 1] != kj);
+	const u32 j0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+	if (j0 >= n) return;
+	u64 prev = j0 ? K[j0 - 1] : ~K[0];
+	u32 w = 0;
+	#pragma unroll
+	for (int b = 0; b < 4; b++) {
+		const u32 j = j0 + b;
+		if (j < n) { const u64 k = K[j]; w |= (k != prev ? 1u : 0u) << (8 * b); prev = k; }
 	}
-	return f;
+	if (j0 + 4 <= n) *reinterpret_cast<u32*>(F + j0) = w;
+	else for (int b = 0; b < 4 && j0 + b < n; b++) F[j0 + b] = (u8)(w >> (8 * b));
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict__ K, const u8* __restrict__ F,
-                                                           const u32* __restrict__ P, u32 A, GAgg* __restrict__ agg)
+__global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u8* __restrict__ F, const u32* __restrict__ AP, u32 A, GAgg* __restrict__ agg)
 {
 	__shared__ i32 smh[8];
 	__shared__ u32 sns[8], sng[8];
@@ -164,10 +184,10 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u64* __restrict
 	for (int s = 0; s < GS_SUB; s++) {
 		const u32 j = base + s * GS_THREADS + t;
 		if (j < A) {
-			const GFlags f = group_flags(K, F, j, A);
-			if (f.head) mh = max(mh, (i32)(P ? P[j] : j));
-			ns += !(f.head && f.nhead);
-			ng += (f.head && !f.nhead);
+			const bool head = F[j] != 0, nhead = (j + 1 == A) || (F[j + 1] != 0);
+			if (head) mh = max(mh, (i32)(AP ? (AP[j] & AP_POS) : j));
+			ns += !(head && nhead);
+			ng += (head && !nhead);
 		}
 	}
 	mh = warp_max(mh); ns = warp_sum(ns); ng = warp_sum(ng);
@@ -228,13 +248,13 @@ __global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg,
 }
 
 // All GS_SUB sub-tiles of a tile are loaded up front (GS_SUB independent loads per array in flight), scanned
-// inside each warp, and stitched together with ONE barrier through a [sub-tile][warp] table -- the earlier
-// one-sub-tile-at-a-time version exposed a full load latency and two barriers per 256 elements (ncu: 93
-// long-scoreboard + 50 barrier stall cycles per issue).
-__global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict__ K, const u8* __restrict__ F, const u32* __restrict__ V,
-                                                          const u32* __restrict__ P, u32 A, const GAgg* __restrict__ agg,
-                                                          int rank_bits, u32* __restrict__ ISA, u32* __restrict__ R, u32* __restrict__ SA,
-                                                          u64* __restrict__ Kn, u32* __restrict__ Vn, u32* __restrict__ Pn)
+// inside each warp, and stitched together with ONE barrier through a [sub-tile][warp] table.
+//   AP == nullptr: the slots are the positions 0..A-1 themselves (the step after the initial sort).
+//   R  != nullptr: ranks leave in slot order (and the suffix ids in VS, if given) for k_isa_scatter to place; R may be
+//                  AP itself -- every thread reads its own slots before it writes them.
+__global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u8* __restrict__ F, const u32* AP, const u32* __restrict__ SA, u32 A,
+                                                          const GAgg* __restrict__ agg, u32* __restrict__ ISA, u32* R, u32* __restrict__ VS,
+                                                          u32* __restrict__ APn)
 {
 	__shared__ i32 wmh[GS_SUB][8];
 	__shared__ u32 wpk[GS_SUB][8];
@@ -248,9 +268,10 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict_
 		const u32 j = base + s * GS_THREADS + t;
 		v[s] = 0; p[s] = 0; fl[s] = 0;
 		if (j < A) {
-			const GFlags f = group_flags(K, F, j, A);
-			fl[s] = 1u | (f.head ? 2u : 0u) | (!(f.head && f.nhead) ? 4u : 0u) | ((f.head && !f.nhead) ? 8u : 0u);
-			v[s] = V[j]; p[s] = P ? P[j] : j;
+			const bool head = F[j] != 0, nhead = (j + 1 == A) || (F[j + 1] != 0);
+			fl[s] = 1u | (head ? 2u : 0u) | (!(head && nhead) ? 4u : 0u) | ((head && !nhead) ? 8u : 0u);
+			p[s] = AP ? (AP[j] & AP_POS) : j;
+			v[s] = SA[p[s]];
 		}
 	}
 	i32 imh[GS_SUB]; u32 ipk[GS_SUB];
@@ -276,12 +297,10 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u64* __restrict_
 		if (fl[s] & 1u) {
 			const i32 fmh = max(imh[s], pm);
 			const u32 fpk = ipk[s] + pp;
-			if (R) R[base + s * GS_THREADS + t] = (u32)fmh + 1u;   // ranks leave in slot order; k_isa_scatter places them
+			const u32 j = base + s * GS_THREADS + t;
+			if (R) { R[j] = (u32)fmh + 1u; if (VS) VS[j] = v[s]; }      // ranks leave in slot order; k_isa_scatter places them
 			else ISA[v[s]] = (u32)fmh + 1u;
-			if (fl[s] & 4u) {
-				const u32 q = carry0.ns + (fpk & 0xffffu) - 1;
-				Vn[q] = v[s]; Pn[q] = p[s]; Kn[q] = (u64)(carry0.ng + (fpk >> 16) - 1) << rank_bits;
-			} else SA[p[s]] = v[s];
+			if (fl[s] & 4u) APn[carry0.ns + (fpk & 0xffffu) - 1] = p[s] | ((fl[s] & 2u) ? AP_HEAD : 0u);
 		}
 		run_mh = tm; run_pk = tp;
 	}
@@ -308,38 +327,18 @@ __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, 
 	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (region_log2 >= 32 || (v[i] >> region_log2) == region)) ISA[v[i]] = r[i];
 }
 
-// ---- 4b. run skip (JP_BWT_FWD_RUNSKIP=1; off by default until measured) --------------------------------
-// Prefix doubling pays one round per doubling of the longest repeat, and the cheapest way to make a long repeat is a
-// run of one symbol (zero pages, padding): a block of n equal bytes takes log2(n / depth) rounds over the whole block.
-// Runs have an exact shortcut. Let r(v) be the length of the run of T[v] that starts at v, and call v a RUN SUFFIX
-// when r(v) >= depth, the number of symbols in the initial key: its key is c^depth, so after the initial sort the run
-// suffixes of a symbol c form one group, and inside it suffix v = c^r(v) X(v), where X(v) starts with a symbol other
-// than c (or is empty). Comparing c^r X with c^r' X', r < r', is decided at position r: X's first symbol against c.
-// Hence the order inside the group is: first the suffixes whose run is followed by a SMALLER symbol (or by the end of
-// the text), by ascending r; then those followed by a larger one, by descending r; ties (equal class and r -- they
-// come from different runs) by the order of the X's. So
-//   * pass A (the first round, h = depth): a run suffix takes key2 = r (first class) or 2n + 1 - r (second class)
-//     instead of ISA[v + h] -- a block of equal bytes is sorted by that one pass -- which leaves its group with equal
-//     (class, r);
-//   * pass B (h still = depth) and every later round: a run suffix with r(v) >= h takes ISA[v + r(v)], the rank of
-//     X(v); one with r(v) < h the ordinary ISA[v + h]. Either way the key is uniform inside a group (its members have
-//     the same r) and the round leaves every suffix at least 2h-ordered, which is the invariant the ordinary keys of
-//     the NEXT round rely on when they read the rank of a position inside a run: c^r X keyed on an h-ordered rank of X
-//     is (r + h)-ordered, and r >= h. (Keying on ISA[v + r] regardless of h looks tempting and is wrong: a run suffix
-//     with r < h would then be less refined than its neighbours assume. Found by the emulated tests.)
-// All other suffixes are untouched. key2 needs one more bit (values up to 2n), which the host accounts for in
-// rank_bits. RL = r(v) for every position, `bits` = bitmap of the run suffixes (read through L2 by the gathers, so
-// only run suffixes pay for the RL gather).
-struct RunSkip { const u32* rl; const u32* bits; const u8* T; u32 first; };
+// ---- 5. doubling rounds ----------------------------------------------------------------------------------
+// key2 of suffix v in the round with offset h. (The template parameter selects the periodic-run keys added below.)
+struct PerSkip { const u32* rl; const u32* bits; const u8* T; u32 p; u32 first; };
 
-template <bool RS>
-__device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restrict__ ISA, const RunSkip& rs, int* __restrict__ err)
+template <bool PS>
+__device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restrict__ ISA, const PerSkip& ps, int* __restrict__ err)
 {
-	if (RS) {
-		if ((__ldg(&rs.bits[v >> 5]) >> (v & 31)) & 1u) {
-			const u32 r = __ldg(&rs.rl[v]);                    // v + r <= n by construction
-			if (rs.first) {
-				const bool smaller_follows = (v + r >= n) || rs.T[v + r] < rs.T[v];
+	if (PS) {
+		if ((__ldg(&ps.bits[v >> 5]) >> (v & 31)) & 1u) {
+			const u32 r = __ldg(&ps.rl[v]);                    // v + r <= n by construction, r >= p
+			if (ps.first) {
+				const bool smaller_follows = (v + r >= n) || ps.T[v + r] < ps.T[v + r - ps.p];
 				return smaller_follows ? r : 2u * n + 1u - r;
 			}
 			if (r >= h) return __ldg(&ISA[v + r]);
@@ -350,103 +349,11 @@ __device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restric
 	return __ldg(&ISA[p]);
 }
 
-constexpr int RUN_TILE = 2048;
-constexpr u32 RUN_NONE = 0xffffffffu;
-__device__ __forceinline__ u32 warp_min_u32(u32 v)
-{
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-	return v;
-}
-
-// last position of the first run that ENDS inside the tile (T[j] != T[j+1], or j == n-1); RUN_NONE if none does
-__global__ void __launch_bounds__(256) k_run_first(const u8* __restrict__ T, u32 n, u32* __restrict__ tile_first)
-{
-	__shared__ u32 wbest[8];
-	const u32 base = blockIdx.x * RUN_TILE;
-	u32 best = RUN_NONE;
-	#pragma unroll
-	for (int i = 0; i < RUN_TILE / 256; i++) {
-		const u32 j = base + i * 256 + threadIdx.x;
-		if (j < n && (j == n - 1 || T[j] != T[j + 1])) best = min(best, j);
-	}
-	best = warp_min_u32(best);
-	if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		#pragma unroll
-		for (int k = 1; k < 8; k++) best = min(best, wbest[k]);
-		tile_first[blockIdx.x] = best;
-	}
-}
-
-// single block: tile_next[t] = first run end in any LATER tile (exclusive suffix minimum)
-__global__ void __launch_bounds__(1024) k_run_scan(const u32* __restrict__ tile_first, u32 tiles, u32* __restrict__ tile_next)
-{
-	__shared__ u32 part[1024];
-	const u32 t = threadIdx.x;
-	const u32 per = (tiles + 1023) / 1024;
-	const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
-	u32 m = RUN_NONE;
-	for (u32 k = lo; k < hi; k++) m = min(m, tile_first[k]);
-	part[t] = m;
-	__syncthreads();
-	u32 run = RUN_NONE;
-	for (u32 k = t + 1; k < 1024; k++) run = min(run, part[k]);
-	for (u32 k = hi; k > lo; k--) { tile_next[k - 1] = run; run = min(run, tile_first[k - 1]); }
-}
-
-// RL[j] = length of the run of T[j] starting at j; bits = (RL[j] >= depth); *count += number of run suffixes
-__global__ void __launch_bounds__(256) k_run_fill(const u8* __restrict__ T, u32 n, const u32* __restrict__ tile_next, u32 depth,
-                                                  u32* __restrict__ RL, u32* __restrict__ bits, u32* __restrict__ count)
-{
-	__shared__ u32 end_at[RUN_TILE];            // first run end at or after each position of the tile
-	__shared__ u32 wfirst[8];
-	const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
-	const u32 base = blockIdx.x * RUN_TILE;
-	// each thread owns 8 consecutive positions: its first run end, if any
-	u32 mine = RUN_NONE;
-	#pragma unroll
-	for (int k = 7; k >= 0; k--) {
-		const u32 j = base + t * 8 + k;
-		if (j < n && (j == n - 1 || T[j] != T[j + 1])) mine = j;
-	}
-	// exclusive suffix minimum over the threads: inside the warp by shuffles, across the 8 warps through shared memory
-	u32 incl = mine;
-	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl = min(incl, x); }
-	u32 excl = __shfl_down_sync(0xffffffffu, incl, 1);
-	if (lane == 31) excl = RUN_NONE;
-	if (lane == 0) wfirst[w] = incl;
-	__syncthreads();
-	u32 carry = min(tile_next[blockIdx.x], excl);
-	for (u32 k = 7; k > w; k--) carry = min(carry, wfirst[k]);
-	#pragma unroll
-	for (int k = 7; k >= 0; k--) {
-		const u32 j = base + t * 8 + k;
-		if (j < n && (j == n - 1 || T[j] != T[j + 1])) carry = j;
-		end_at[t * 8 + k] = carry;
-	}
-	__syncthreads();
-	u32 cnt = 0;
-	#pragma unroll
-	for (int i = 0; i < RUN_TILE / 256; i++) {
-		const u32 j = base + i * 256 + t;
-		u32 r = 0;
-		if (j < n) { r = end_at[i * 256 + t] - j + 1; RL[j] = r; }
-		const u32 m = __ballot_sync(0xffffffffu, j < n && r >= depth);
-		if (lane == 0 && base + i * 256 + (t & ~31u) < n) { bits[(base + i * 256 + t) >> 5] = m; cnt += __popc(m); }
-	}
-	if (lane == 0 && cnt) atomicAdd(count, cnt);
-}
-
-// ---- 5a. doubling round, small groups: gather + segmented sort in shared memory -------------------------
+// ---- 5a. small groups: gather + segmented sort in shared memory -----------------------------------------
 // Groups are contiguous in the active set, so refining them is a SEGMENTED sort. Block c owns the groups whose
 // head lies in its window of SG_WIN slots; they end within two windows unless the last one is "large". The block
-// gathers key2 = ISA[s + h] for its (<= 4096) elements, sorts (local group id, key2) with an LSD radix sort that
-// never leaves shared memory (warp match.any ranking, same scheme as k_rs_scatter), writes the suffix ids back in
-// place and one head flag per element. One global read and one global write of 4 bytes per active suffix
-// replace the 7 global radix passes over 12-byte pairs of the composite-key route.
+// gathers key2 for its (<= 4096) elements, orders every group by key2 in shared memory, writes the suffix ids back
+// to their group's positions of SA and one head flag per slot.
 constexpr int SG_THREADS = 256;
 constexpr int SG_ITEMS   = 16;
 constexpr int SG_CAP     = SG_THREADS * SG_ITEMS;   // 4096 elements sorted per block
@@ -459,7 +366,7 @@ struct SegTile { u32 start, len; };
 // Slot range [start, start+len) of the groups whose head lies in window `win` (len == 0: nothing to do).
 // When `win_first` is given, the block also records its first head slot and the head of the group it had to
 // leave to the large-group route (0xffffffff = none); k_large_collect turns those into the list of large groups.
-__device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K, u32 A, int rank_bits,
+__device__ __forceinline__ SegTile seg_range(u32 win, const u32* __restrict__ AP, u32 A,
                                              u32* __restrict__ sh /*[3]*/, u32* __restrict__ has_large,
                                              u32* __restrict__ win_first = nullptr, u32* __restrict__ win_large = nullptr)
 {
@@ -472,10 +379,7 @@ __device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K,
 	#pragma unroll
 	for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
 		const u32 j = w0 + i * SG_THREADS + t;
-		if (j < L) {
-			const u64 g = K[j] >> rank_bits;
-			if (j == 0 || (K[j - 1] >> rank_bits) != g) { atomicMin(&sh[0], j); atomicMax(&sh[1], j); }
-		}
+		if (j < L && (j == 0 || (AP[j] & AP_HEAD))) { atomicMin(&sh[0], j); atomicMax(&sh[1], j); }
 	}
 	__syncthreads();
 	const u32 start = sh[0];
@@ -484,12 +388,11 @@ __device__ __forceinline__ SegTile seg_range(u32 win, const u64* __restrict__ K,
 	u32 end;
 	if (L == A) end = A;
 	else {
-		const u64 gl = K[L - 1] >> rank_bits;
 		const u32 lim = min(w0 + 2u * SG_WIN, A);
 		#pragma unroll
 		for (int i = 0; i < SG_WIN / SG_THREADS; i++) {
 			const u32 j = L + i * SG_THREADS + t;
-			if (j < lim && (K[j] >> rank_bits) != gl) atomicMin(&sh[2], j);
+			if (j < lim && (AP[j] & AP_HEAD)) atomicMin(&sh[2], j);
 		}
 		__syncthreads();
 		end = sh[2];
@@ -518,21 +421,21 @@ __device__ __forceinline__ u32 warp_rev_incl_min(u32 v)
 // scans (last head at or before me / first group end at or after me) stitched across the block through a small
 // table with a single barrier; then it counts the members of its group that sort before it.
 constexpr size_t SG_SMEM_LIGHT = (size_t)SG_CAP * (4 + 4 + 1);
-template <bool RS>
-__global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
-                                                         const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+template <bool PS>
+__global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u32* __restrict__ AP, u32* __restrict__ SA, u32 A,
+                                                         const u32* __restrict__ ISA, u32 h, u32 n,
                                                          u8* __restrict__ F, u32* __restrict__ counters /*[2]=has_large [3]=queued*/,
                                                          u32* __restrict__ queue, u32* __restrict__ win_first, u32* __restrict__ win_large,
-                                                         int* __restrict__ err, RunSkip rs)
+                                                         int* __restrict__ err, PerSkip ps)
 {
 	extern __shared__ __align__(16) u8 sg_smem[];
-	u32* skey = reinterpret_cast<u32*>(sg_smem);        // key2 = ISA[s + h]; later the refined suffix ids
+	u32* skey = reinterpret_cast<u32*>(sg_smem);        // key2; later the refined suffix ids
 	u32* sval = skey + SG_CAP;                          // suffix ids in slot order
 	u8* sflag = reinterpret_cast<u8*>(sval + SG_CAP);   // head flags of the refined order
 	__shared__ u32 sh[3];
 	__shared__ u32 wf[SG_ITEMS][SG_THREADS / 32], wb[SG_ITEMS][SG_THREADS / 32];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	const SegTile tile = seg_range(blockIdx.x, K, A, rank_bits, sh, counters + 2, win_first, win_large);
+	const SegTile tile = seg_range(blockIdx.x, AP, A, sh, counters + 2, win_first, win_large);
 	const u32 len = tile.len, start = tile.start;
 	if (len == 0) return;
 
@@ -545,12 +448,12 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restric
 		u32 hl = 0;
 		if (e < len) {
 			const u32 j = start + e;
-			const u32 v = V[j];
-			const u64 g = K[j] >> rank_bits;
-			const bool head = (e == 0) || (K[j - 1] >> rank_bits) != g;
-			const bool last = (e == len - 1) || (K[j + 1] >> rank_bits) != g;
+			const u32 ap = AP[j];
+			const bool head = (e == 0) || (ap & AP_HEAD);
+			const bool last = (e == len - 1) || (AP[j + 1] & AP_HEAD);
+			const u32 v = SA[ap & AP_POS];
 			sval[e] = v;
-			skey[e] = key2_of<RS>(v, h, n, ISA, rs, err);
+			skey[e] = key2_of<PS>(v, h, n, ISA, ps, err);
 			hl = (head ? 1u : 0u) | (last ? 2u : 0u) | 4u;
 		}
 		const u32 f = warp_incl_max((hl & 1u) ? (i32)e : 0);
@@ -611,15 +514,15 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u64* __restric
 	#pragma unroll
 	for (int i = 0; i < SG_ITEMS; i++) {
 		const u32 e = i * SG_THREADS + t;
-		if (e < len) { V[start + e] = skey[e]; F[start + e] = sflag[e]; }
+		if (e < len) { SA[AP[start + e] & AP_POS] = skey[e]; F[start + e] = sflag[e]; }
 	}
 }
 
-// Radix route for the queued tiles: LSD radix sort of (local group id, key2) that never leaves shared memory.
-template <bool RS>
-__global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __restrict__ K, u32* __restrict__ V, u32 A,
+// Radix route for the queued tiles: LSD radix sort of (local group number, key2) that never leaves shared memory.
+template <bool PS>
+__global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u32* __restrict__ AP, u32* __restrict__ SA, u32 A,
                                                                const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
-                                                               u8* __restrict__ F, const u32* __restrict__ queue, int* __restrict__ err, RunSkip rs)
+                                                               u8* __restrict__ F, const u32* __restrict__ queue, int* __restrict__ err, PerSkip ps)
 {
 	extern __shared__ __align__(16) u8 sg_smem[];
 	u64* skey = reinterpret_cast<u64*>(sg_smem);
@@ -630,25 +533,36 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __rest
 	__shared__ u32 sh[3];
 	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
 	const u32 lt = lanemask_lt();
-	const SegTile tile = seg_range(queue[blockIdx.x], K, A, rank_bits, sh, nullptr);
+	const SegTile tile = seg_range(queue[blockIdx.x], AP, A, sh, nullptr);
 	const u32 len = tile.len, start = tile.start;
 	if (len == 0) return;
-	{
-		const u64 g0 = K[start] >> rank_bits;
-		#pragma unroll 4
-		for (int i = 0; i < SG_ITEMS; i++) {
-			const u32 e = i * SG_THREADS + t;
-			if (e < len) {
-				const u32 j = start + e;
-				const u32 v = V[j];
-				const u32 k2 = key2_of<RS>(v, h, n, ISA, rs, err);
-				sval[e] = v;
-				skey[e] = (((K[j] >> rank_bits) - g0) << 32) | (u64)k2;
-			}
+	#pragma unroll 4
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 e = i * SG_THREADS + t;
+		if (e < len) {
+			const u32 ap = AP[start + e];
+			const u32 v = SA[ap & AP_POS];
+			sval[e] = v;
+			skey[e] = ((u64)((e == 0 || (ap & AP_HEAD)) ? 1u : 0u) << 32) | (u64)key2_of<PS>(v, h, n, ISA, ps, err);
 		}
+	}
+	__syncthreads();
+	// local group number = heads at or before the element, minus one: each thread counts its 16 consecutive slots
+	u32 gmax;
+	{
+		u32 mine = 0;
+		#pragma unroll
+		for (int k = 0; k < SG_ITEMS; k++) { const u32 e = t * SG_ITEMS + k; if (e < len) mine += (u32)(skey[e] >> 32); }
+		u32 total;
+		u32 g = block_incl_sum(mine, ws, &total) - mine;
+		#pragma unroll
+		for (int k = 0; k < SG_ITEMS; k++) {
+			const u32 e = t * SG_ITEMS + k;
+			if (e < len) { const u64 c = skey[e]; g += (u32)(c >> 32); skey[e] = ((u64)(g - 1) << 32) | (c & 0xffffffffull); }
+		}
+		gmax = total - 1;
 		__syncthreads();
 	}
-	const u32 gmax = (u32)(skey[len - 1] >> 32);
 	const int bits = rank_bits + bit_length((u64)gmax);
 	u64 key[SG_ITEMS];
 	u32 val[SG_ITEMS];
@@ -705,18 +619,17 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_sort_radix(const u64* __rest
 	for (int i = 0; i < SG_ITEMS; i++) {
 		const u32 e = w * (32 * SG_ITEMS) + i * 32 + lane;
 		if (e < len) {
-			V[start + e] = val[i];
+			SA[AP[start + e] & AP_POS] = val[i];
 			F[start + e] = (e == 0 || skey[e - 1] != key[i]) ? 1 : 0;
 		}
 	}
 }
 
-// ---- 5b. doubling round, large groups -------------------------------------------------------------------
+// ---- 5b. large groups -----------------------------------------------------------------------------------
 // A group longer than a window (common prefixes of real text, periodic data) cannot be sorted inside one block.
 // The windows report where such groups start; k_large_collect finds where they end (the next group head of any
-// later window) and lays them out back to back; their suffixes are extracted with key (large-group id, ISA[s+h]),
-// sorted by the global radix sort, and written back in place with their head flags. Everything else in the
-// active set stays on the shared-memory route.
+// later window) and lays them out back to back; their suffixes are extracted with key (large-group number, key2),
+// sorted by the global radix sort, and written back in place with their head flags.
 __global__ void __launch_bounds__(1024) k_large_collect(u32* __restrict__ win_first, const u32* __restrict__ win_large, u32 nwin, u32 A,
                                                         u32* __restrict__ lg_head, u32* __restrict__ lg_off, u32* __restrict__ counters /*[4] groups [5] elements*/)
 {
@@ -759,23 +672,23 @@ __device__ __forceinline__ u32 large_group_of(const u32* __restrict__ lg_off, u3
 	return lo;
 }
 
-template <bool RS>
-__global__ void __launch_bounds__(256) k_large_extract(const u32* __restrict__ V, const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
+template <bool PS>
+__global__ void __launch_bounds__(256) k_large_extract(const u32* __restrict__ AP, const u32* __restrict__ SA, const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
                                                        const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 ng, u32 total,
-                                                       u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err, RunSkip rs)
+                                                       u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err, PerSkip ps)
 {
 	const u32 x = blockIdx.x * 256 + threadIdx.x;
 	if (x >= total) return;
 	const u32 g = large_group_of(lg_off, ng, x);
-	const u32 v = V[lg_head[g] + (x - lg_off[g])];
-	const u32 k2 = key2_of<RS>(v, h, n, ISA, rs, err);
+	const u32 v = SA[AP[lg_head[g] + (x - lg_off[g])] & AP_POS];
+	const u32 k2 = key2_of<PS>(v, h, n, ISA, ps, err);
 	LK[x] = ((u64)g << rank_bits) | (u64)k2;
 	LV[x] = v;
 }
 
 __global__ void __launch_bounds__(256) k_large_writeback(const u64* __restrict__ LK, const u32* __restrict__ LV, int rank_bits,
                                                          const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 total,
-                                                         u32* __restrict__ V, u8* __restrict__ F)
+                                                         const u32* __restrict__ AP, u32* __restrict__ SA, u8* __restrict__ F)
 {
 	const u32 x = blockIdx.x * 256 + threadIdx.x;
 	if (x >= total) return;
@@ -783,18 +696,8 @@ __global__ void __launch_bounds__(256) k_large_writeback(const u64* __restrict__
 	const u32 g = (u32)(k >> rank_bits);
 	const u32 o = lg_off[g];
 	const u32 slot = lg_head[g] + (x - o);
-	V[slot] = LV[x];
+	SA[AP[slot] & AP_POS] = LV[x];
 	F[slot] = (x == o || LK[x - 1] != k) ? 1 : 0;
-}
-
-// ---- 5c. doubling round, composite-key route for the whole active set (A/B reference: JP_BWT_FWD_GLOBAL=1) ---------------------------------------------------
-template <bool RS>
-__global__ void __launch_bounds__(256) k_fwd_gather(u64* __restrict__ K, const u32* __restrict__ V, u32 A,
-                                                    const u32* __restrict__ ISA, u32 h, u32 n, int* __restrict__ err, RunSkip rs)
-{
-	const u32 j = blockIdx.x * 256 + threadIdx.x;
-	if (j >= A) return;
-	K[j] |= (u64)key2_of<RS>(V[j], h, n, ISA, rs, err);
 }
 
 // ---- 6. emission ---------------------------------------------------------------------------------------
@@ -836,12 +739,12 @@ __global__ void k_fwd_trailer(const u8* __restrict__ T, const u32* __restrict__ 
 
 // ---- host driver ---------------------------------------------------------------------------------------
 struct FwdBuffers {
-	RadixBuffers rb;
-	u32* P[2];
-	u32* ISA; u32* SA; u32* R;
-	u32* RL; u32* run_bits; u32* run_first; u32* run_next; u32* run_count;   // run skip (null when off)
+	size_t usz;                // bytes per unit: room for N + 2 32-bit words
+	u8* unit[6];
+	RadixBuffers rb;           // initial sort: k[0] = units 0-1, k[1] = units 2-3, v[0] = unit 4, v[1] = unit 5
+	u32* SA; u32* ISA; u32* VS; u32* X; u32* AP[2];   // roles of the six units once the initial sort is done
+	u8* F;                     // one byte per slot (next-digit bytes, then head flags): the caller's output block
 	int isa_region_log2;
-	u8* F;
 	u32* queue;
 	u32* win_first; u32* win_large; u32* lg_head; u32* lg_off;
 	GAgg* agg;
@@ -850,38 +753,36 @@ struct FwdBuffers {
 	int* err;
 };
 
-static bool runskip_enabled()
-{
-	const char* e = getenv("JP_BWT_FWD_RUNSKIP");
-	return e != nullptr && atoi(e) != 0;
-}
-
-static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
+static size_t fwd_bytes(i32 n, bool own_flags)
 {
 	const size_t N = (size_t)n;
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
-	size_t total = 2 * Arena::align(N * 8) + 4 * Arena::align(N * 4) + Arena::align((N + 1) * 4) + 2 * Arena::align(N * 4) +
-	               Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) + Arena::align(N + 64) + Arena::align(gtiles * sizeof(GAgg)) +
-	               Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) + Arena::align(N + 16) + 5 * Arena::align((N / SG_WIN + 16) * 4);
-	const bool runskip = runskip_enabled();
-	const size_t run_tiles = (N + RUN_TILE - 1) / RUN_TILE;
-	if (runskip) total += Arena::align(N * 4) + Arena::align((N / 32 + 2) * 4) + 2 * Arena::align((run_tiles + 1) * 4) + Arena::align(64);
-	JP_TRY(arena_reserve(c, total));
-	b.rb.k[0] = arena_take<u64>(c, N); b.rb.k[1] = arena_take<u64>(c, N);
-	b.rb.v[0] = arena_take<u32>(c, N); b.rb.v[1] = arena_take<u32>(c, N);
-	b.P[0] = arena_take<u32>(c, N); b.P[1] = arena_take<u32>(c, N);
-	b.ISA = arena_take<u32>(c, N + 1); b.SA = arena_take<u32>(c, N); b.R = arena_take<u32>(c, N);
+	return 6 * Arena::align((N + 2) * 4) + Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) +
+	       Arena::align(gtiles * sizeof(GAgg)) + Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) +
+	       5 * Arena::align((N / SG_WIN + 16) * 4) + (own_flags ? Arena::align(N + 64) : 0);
+}
+
+// d_flags: N bytes of scratch that stay untouched until the suffix array is complete (the output block), or nullptr
+static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b, u8* d_flags)
+{
+	const size_t N = (size_t)n;
+	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
+	JP_TRY(arena_reserve(c, fwd_bytes(n, d_flags == nullptr)));
+	b.usz = Arena::align((N + 2) * 4);
+	for (int i = 0; i < 6; i++) b.unit[i] = arena_take<u8>(c, b.usz);
+	b.rb.k[0] = reinterpret_cast<u64*>(b.unit[0]); b.rb.k[1] = reinterpret_cast<u64*>(b.unit[2]);
+	b.rb.v[0] = reinterpret_cast<u32*>(b.unit[4]); b.rb.v[1] = reinterpret_cast<u32*>(b.unit[5]);
 	b.isa_region_log2 = 24;                            // 2^24 ranks = 64 MiB of ISA per pass (measured best of 2^21..2^25)
 	if (const char* e = getenv("JP_BWT_ISA_REGION_LOG2")) b.isa_region_log2 = atoi(e);
 	b.rb.tile_hist = arena_take<u32>(c, (rtiles + 4) * 256);
 	b.rb.totals = arena_take<u32>(c, 256);
 	b.rb.os_state = arena_take<u32>(c, 8 * 256 + 64);
-	b.rb.dnext = getenv("JP_BWT_RADIX_NO_DIGIT_BYTES") ? nullptr : arena_take<u8>(c, N + 64);
+	b.F = d_flags ? d_flags : arena_take<u8>(c, N + 64);
+	b.rb.dnext = getenv("JP_BWT_RADIX_NO_DIGIT_BYTES") ? nullptr : b.F;
 	// Measured on B200 (64 M pairs, 8 passes): three-kernel passes 5.07 ms, one-sweep (all digits counted in one read of
 	// the keys + 8 look-back passes) 6.18 ms -- with ~440 tiles in flight the per-digit look-back chain costs more than
 	// the key re-read it saves, so the classic pass is the default.
 	b.rb.classic = getenv("JP_BWT_RADIX_ONESWEEP") == nullptr;
-	b.F = arena_take<u8>(c, N + 16);
 	b.queue = arena_take<u32>(c, N / SG_WIN + 16);
 	b.win_first = arena_take<u32>(c, N / SG_WIN + 16); b.win_large = arena_take<u32>(c, N / SG_WIN + 16);
 	b.lg_head = arena_take<u32>(c, N / SG_WIN + 16); b.lg_off = arena_take<u32>(c, N / SG_WIN + 16);
@@ -890,41 +791,53 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b)
 	b.counters = arena_take<u32>(c, 16);
 	b.err = arena_take<int>(c, 16);
 	b.rb.err = b.err;
-	b.RL = b.run_bits = b.run_first = b.run_next = b.run_count = nullptr;
-	if (runskip) {
-		b.RL = arena_take<u32>(c, N); b.run_bits = arena_take<u32>(c, N / 32 + 2);
-		b.run_first = arena_take<u32>(c, run_tiles + 1); b.run_next = arena_take<u32>(c, run_tiles + 1);
-		b.run_count = arena_take<u32>(c, 16);
+	b.SA = b.ISA = b.VS = b.X = b.AP[0] = b.AP[1] = nullptr;
+	return JP_OK;
+}
+
+// ISA[V[j]] = R[j] for the A slots, staged by region (k_isa_scatter). `pv`/`pr`: room for `pcap` entries each, used when the
+// block has too many regions for per-region sweeps: the pairs are bucketed by region first, `pcap` slots at a time.
+static int place_ranks(Ctx& c, FwdBuffers& b, const u32* V, const u32* R, u32 A, u32* pv, u32* pr, u32 pcap, cudaStream_t s)
+{
+	const u32 n_entries = c.cur_n + 1, regions = (n_entries + (1u << b.isa_region_log2) - 1) >> b.isa_region_log2;
+	if (regions <= 4 || regions > 256) {
+		// few regions: stream the slots once per region and keep the ranks that fall in it
+		const u32 stiles = (A + 2047) / 2048;
+		k_isa_scatter<<<regions * stiles, 256, 0, s>>>(V, R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
+		return JP_OK;
+	}
+	// many regions (blocks over 64 MiB): one radix partition pass buckets the (suffix, rank) pairs by region, then a
+	// single ordered sweep
+	for (u32 off = 0; off < A; off += pcap) {
+		const u32 cnt = std::min(pcap, A - off);
+		if (radix_partition_u32(V + off, R + off, pv, pr, cnt, b.isa_region_log2, b.rb.tile_hist, b.rb.totals, s, &c.launches) != 0) { set_error_detail("radix partition setup failed"); return JP_ERR_CUDA; }
+		const u32 stiles = (cnt + 2047) / 2048;
+		k_isa_scatter<<<stiles, 256, 0, s>>>(pv, pr, cnt, b.ISA, 32, stiles); JP_LAUNCH(c);
 	}
 	return JP_OK;
 }
 
-// One grouping step over the sorted pairs in rb.k/v[cur]; survivors land in rb.k/v[cur^1] and P[pc^1].
-static int group_step(Ctx& c, FwdBuffers& b, int cur, int pc, bool identity_pos, bool use_flags, u32 A, int rank_bits, cudaStream_t s)
+// One grouping step over the A slots of APin (nullptr: the N positions themselves) with head flags b.F; survivors land in
+// APout. Leaves the survivor and group counts in h_small[8..9] and the device error flag in h_small[0].
+static int group_step(Ctx& c, FwdBuffers& b, const u32* APin, u32* APout, u32 A, cudaStream_t s)
 {
 	const int tiles = (int)((A + GS_TILE - 1) / GS_TILE);
-	const u32* P = identity_pos ? nullptr : b.P[pc];
-	const u8* F = use_flags ? b.F : nullptr;
-	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, P, A, b.agg); JP_LAUNCH(c);
+	k_grp_reduce<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, A, b.agg); JP_LAUNCH(c);
 	k_grp_scan_tiles<<<1, 1024, 0, s>>>(b.agg, tiles, b.counters); JP_LAUNCH(c);
 	// small active sets (and the A/B switch region_log2 <= 0) scatter straight from the apply kernel
-	const bool staged = b.isa_region_log2 > 0 && A > (1u << 20);
-	k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.rb.k[cur], F, b.rb.v[cur], P, A, b.agg, rank_bits, b.ISA, staged ? b.R : nullptr, b.SA,
-	                                          b.rb.k[cur ^ 1], b.rb.v[cur ^ 1], b.P[pc ^ 1]); JP_LAUNCH(c);
-	if (staged) {
-		const u32 n_entries = c.cur_n + 1, regions = (n_entries + (1u << b.isa_region_log2) - 1) >> b.isa_region_log2;
-		const u32 stiles = (A + 2047) / 2048;
-		if (regions <= 4 || regions > 256) {
-			// few regions: stream the slots once per region and keep the ranks that fall in it
-			k_isa_scatter<<<regions * stiles, 256, 0, s>>>(b.rb.v[cur], b.R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
-		} else {
-			// many regions (blocks over 64 MiB): one radix partition pass buckets the (suffix, rank) pairs by region -- the
-			// sorted keys of this step are dead, their buffer holds the bucketed pairs -- then a single ordered sweep
-			u32* pv = reinterpret_cast<u32*>(b.rb.k[cur]);
-			u32* pr = pv + A;
-			if (radix_partition_u32(b.rb.v[cur], b.R, pv, pr, A, b.isa_region_log2, b.rb.tile_hist, b.rb.totals, s, &c.launches) != 0) { set_error_detail("radix partition setup failed"); return JP_ERR_CUDA; }
-			k_isa_scatter<<<stiles, 256, 0, s>>>(pv, pr, A, b.ISA, 32, stiles); JP_LAUNCH(c);
-		}
+	const u32 stage_min = getenv("JP_BWT_ISA_STAGE_MIN") ? (u32)atol(getenv("JP_BWT_ISA_STAGE_MIN")) : (1u << 20);   // (tests lower it)
+	const bool staged = b.isa_region_log2 > 0 && A > stage_min;
+	if (!staged) { k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, nullptr, nullptr, APout); JP_LAUNCH(c); }
+	else if (APin == nullptr) {
+		// initial step: the suffix ids are SA itself; ranks go to the spare unit; VS and the second active buffer are free
+		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, nullptr, b.SA, A, b.agg, b.ISA, b.X, nullptr, APout); JP_LAUNCH(c);
+		JP_TRY(place_ranks(c, b, b.SA, b.X, A, b.VS, APout == b.AP[0] ? b.AP[1] : b.AP[0], (u32)(b.usz / 4), s));
+	} else {
+		// a round: ranks overwrite the (dead) input slots, suffix ids are staged in VS; the spare unit holds the bucketed pairs
+		u32* R = const_cast<u32*>(APin);
+		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, R, b.VS, APout); JP_LAUNCH(c);
+		const u32 half = (u32)(b.usz / 8);
+		JP_TRY(place_ranks(c, b, b.VS, R, A, b.X, b.X + half, half, s));
 	}
 	JP_KCHECK();
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 8, b.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -939,7 +852,6 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	c.cur_n = (u32)n;
 	JP_CUDA(cudaMemsetAsync(b.meta, 0, sizeof(FwdMeta), s));
 	JP_CUDA(cudaMemsetAsync(b.err, 0, 64, s));
-	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
 	const i64 hwant = ((i64)n + 4095) / 4096, hcap = (i64)c.sm_count * 8;
 	const int hblocks = (int)(hwant < hcap ? hwant : hcap);
 	k_fwd_symhist<<<hblocks, 256, 0, s>>>(d_T, n, b.meta); JP_LAUNCH(c);
@@ -954,121 +866,102 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
 	                                                         rs_stride((u32)radix_tiles((size_t)n))); JP_LAUNCH(c);
 	JP_KCHECK();
-	const bool runskip = b.RL != nullptr;                                // JP_BWT_FWD_RUNSKIP=1 (see "run skip" above)
-	if (runskip) {
-		const u32 run_tiles = (u32)(((size_t)n + RUN_TILE - 1) / RUN_TILE);
-		JP_CUDA(cudaMemsetAsync(b.run_count, 0, 64, s));
-		k_run_first<<<run_tiles, 256, 0, s>>>(d_T, (u32)n, b.run_first); JP_LAUNCH(c);
-		k_run_scan<<<1, 1024, 0, s>>>(b.run_first, run_tiles, b.run_next); JP_LAUNCH(c);
-		k_run_fill<<<run_tiles, 256, 0, s>>>(d_T, (u32)n, b.run_next, (u32)depth, b.RL, b.run_bits, b.run_count); JP_LAUNCH(c);
-		JP_KCHECK();
-		JP_CUDA(cudaMemcpyAsync(c.h_small + 14, b.run_count, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the first group step's sync
-	}
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
-	const bool force_global = getenv("JP_BWT_FWD_GLOBAL") != nullptr;    // A/B switch: composite-key route for every round
 	if (cudaFuncSetAttribute(k_seg_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
-	int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/true);
+	const int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/true);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
 
-	const int rank_bits = bit_length(runskip ? 2 * (u64)n + 1 : (u64)n);   // key2 is a rank <= n, or a run key <= 2n
-	int pc = 0;
-	JP_TRY(group_step(c, b, cur, pc, true, false, (u32)n, rank_bits, s));
-	const bool use_rs = runskip && c.h_small[14] != 0;                   // no run suffix in this block: the plain kernels
-	RunSkip rs; rs.rl = b.RL; rs.bits = b.run_bits; rs.T = d_T; rs.first = 1;
+	// The sorted suffix ids are the suffix array from here on; the key buffers and the other id buffer take new roles
+	// (the keys are read one last time, for the head flags).
+	b.SA = b.rb.v[cur];
+	k_fwd_flags<<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+	b.ISA = reinterpret_cast<u32*>(b.unit[cur ? 0 : 2]);      // first half of the other key buffer
+	b.X = reinterpret_cast<u32*>(b.unit[cur ? 1 : 3]);        // ... and its second half
+	b.AP[0] = reinterpret_cast<u32*>(b.unit[cur ? 2 : 0]);    // the sorted keys' own buffer, dead once the flags exist
+	b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
+	b.VS = b.rb.v[cur ^ 1];
+	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
+	const int rank_bits = bit_length((u64)n);                           // key2 is a rank <= n
+	JP_TRY(group_step(c, b, nullptr, b.AP[0], (u32)n, s));
+	PerSkip ps; ps.rl = nullptr; ps.bits = nullptr; ps.T = d_T; ps.p = 1; ps.first = 0;
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
-	int act = cur ^ 1; pc ^= 1;
+	int act = 0;
 	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
 	u64 sectors = 2ull * (u64)n;
 	i64 h = depth;
 	int rounds = 0;
-	double large_frac_prev = 0.0;
 	const bool trace_rounds = getenv("JP_BWT_TRACE_ROUNDS") != nullptr;      // one stderr line per doubling round (host wall time)
 	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	while (A > 0) {
 		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
-		rs.first = rounds == 0 ? 1u : 0u;                                // run skip: pass A, then pass B at the same h
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
 		st->active_fraction[rounds] = (float)((double)A / (double)n);
 		sectors += 2ull * A;
 		double large_frac_now = 0.0;
-		// a round that had most of the block in over-long groups (periodic data, one-symbol runs) is followed by more
-		// of the same: skip the shared-memory kernels and sort the whole active set by composite key
-		if (!force_global && large_frac_prev <= 0.5) {
-			// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
-			// shared-memory radix kernel; groups longer than a window are reported for the large-group route
-			const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
-			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
-			if (use_rs) k_seg_sort<true><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
-			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err, rs);
-			else k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, rank_bits, b.F,
-			                                                   b.counters, b.queue, b.win_first, b.win_large, b.err, rs);
+		const u32* AP = b.AP[act];
+		// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
+		// shared-memory radix kernel; groups longer than a window are reported for the large-group route
+		const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
+		JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
+		k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
+		JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		const bool large = c.h_small[10] != 0;
+		const u32 queued = (u32)c.h_small[11];
+		if (queued) {
+			k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
 			JP_LAUNCH(c);
 			JP_KCHECK();
-			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-			JP_CUDA(cudaStreamSynchronize(s));
-			const bool large = c.h_small[10] != 0;
-			const u32 queued = (u32)c.h_small[11];
-			if (queued) {
-				if (use_rs) k_seg_sort_radix<true><<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
-				                                                    rank_bits, b.F, b.queue, b.err, rs);
-				else k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n,
-				                                                    rank_bits, b.F, b.queue, b.err, rs);
-				JP_LAUNCH(c);
-				JP_KCHECK();
-				st->ms_phase[6] += (float)queued;       // tiles that needed the shared-memory radix route
-			}
-			if (large) {
-				k_large_collect<<<1, 1024, 0, s>>>(b.win_first, b.win_large, nwin, A, b.lg_head, b.lg_off, b.counters); JP_LAUNCH(c);
-				JP_KCHECK();
-				JP_CUDA(cudaMemcpyAsync(c.h_small + 12, b.counters + 4, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-				JP_CUDA(cudaStreamSynchronize(s));
-				const u32 ng = (u32)c.h_small[12], total = (u32)c.h_small[13];
-				st->ms_phase[5] += (float)((double)total / (double)n);   // fraction of the block that went through the large-group route, summed over rounds
-				large_frac_now = (double)total / (double)A;
-				if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
-				// the gidx keys of the active set are dead once the shared-memory kernels are done: sort in the spare buffers
-				RadixBuffers lb = b.rb;
-				lb.k[0] = b.rb.k[act ^ 1]; lb.k[1] = b.rb.k[act];
-				lb.v[0] = b.rb.v[act ^ 1]; lb.v[1] = b.R;
-				if (use_rs) k_large_extract<true><<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
-				                                                    lb.k[0], lb.v[0], b.err, rs);
-				else k_large_extract<false><<<(total + 255) / 256, 256, 0, s>>>(b.rb.v[act], b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
-				                                                    lb.k[0], lb.v[0], b.err, rs);
-				JP_LAUNCH(c);
-				const int key_bits = rank_bits + bit_length((u64)(ng - 1));
-				const int lc = radix_sort_pairs(lb, 0, total, 0, key_bits, s, &c.launches);
-				if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-				k_large_writeback<<<(total + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, total, b.rb.v[act], b.F); JP_LAUNCH(c);
-				JP_KCHECK();
-			}
-			cur = act;
-			JP_TRY(group_step(c, b, cur, pc, false, true, A, rank_bits, s));
-		} else {
-			st->ms_phase[5] += (float)((double)A / (double)n);
-			large_frac_now = G * (u64)SG_WIN >= A ? 0.0 : 1.0;       // back to the segmented route once groups average under a window
-			if (use_rs) k_fwd_gather<true><<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err, rs);
-			else k_fwd_gather<false><<<(A + 255) / 256, 256, 0, s>>>(b.rb.k[act], b.rb.v[act], A, b.ISA, (u32)h, (u32)n, b.err, rs);
-			JP_LAUNCH(c);
-			const int key_bits = rank_bits + bit_length((u64)(G > 0 ? G - 1 : 0));
-			cur = radix_sort_pairs(b.rb, act, A, 0, key_bits, s, &c.launches);
-			if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-			JP_TRY(group_step(c, b, cur, pc, false, false, A, rank_bits, s));
+			st->radix_tiles += (i32)queued;
 		}
+		if (large) {
+			k_large_collect<<<1, 1024, 0, s>>>(b.win_first, b.win_large, nwin, A, b.lg_head, b.lg_off, b.counters); JP_LAUNCH(c);
+			JP_KCHECK();
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 12, b.counters + 4, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaStreamSynchronize(s));
+			const u32 ng = (u32)c.h_small[12], total = (u32)c.h_small[13];
+			st->large_fraction += (float)((double)total / (double)n);   // share of the block on the large-group route, summed over rounds
+			large_frac_now = (double)total / (double)A;
+			if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
+			// scratch of the sort: the spare unit, the staging unit and the idle active buffer hold (8 + 8 + 2 x 4) bytes for
+			// up to N/2 suffixes; beyond that (blocks that are mostly long repeats) the second arena provides
+			RadixBuffers lb = b.rb;
+			lb.dnext = nullptr;                             // the flag bytes of this round are live in b.F
+			if ((size_t)total * 8 <= b.usz) {
+				lb.k[0] = reinterpret_cast<u64*>(b.X); lb.k[1] = reinterpret_cast<u64*>(b.VS);
+				lb.v[0] = b.AP[act ^ 1]; lb.v[1] = b.AP[act ^ 1] + b.usz / 8;
+			} else {
+				const size_t T8 = Arena::align((size_t)total * 8), T4 = Arena::align((size_t)total * 4);
+				JP_TRY(arena2_reserve(c, 2 * T8 + 2 * T4));
+				lb.k[0] = reinterpret_cast<u64*>(c.arena2.base); lb.k[1] = reinterpret_cast<u64*>(c.arena2.base + T8);
+				lb.v[0] = reinterpret_cast<u32*>(c.arena2.base + 2 * T8); lb.v[1] = reinterpret_cast<u32*>(c.arena2.base + 2 * T8 + T4);
+			}
+			k_large_extract<false><<<(total + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
+			                                                    lb.k[0], lb.v[0], b.err, ps);
+			JP_LAUNCH(c);
+			const int key_bits = rank_bits + bit_length((u64)(ng - 1));
+			const int lc = radix_sort_pairs(lb, 0, total, 0, key_bits, s, &c.launches);
+			if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+			k_large_writeback<<<(total + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, total, AP, b.SA, b.F); JP_LAUNCH(c);
+			JP_KCHECK();
+		}
+		JP_TRY(group_step(c, b, AP, b.AP[act ^ 1], A, s));
 		if (trace_rounds) {
 			const double t1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 			fprintf(stderr, "[jp_bwt round] %d h=%lld active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h, A, G,
 			        (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
 			t_round = t1;
 		}
-		act = cur ^ 1; pc ^= 1;
+		act ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
-		large_frac_prev = large_frac_now;
-		if (!(use_rs && rounds == 0)) h *= 2;
+		h *= 2;
 		rounds++;
 	}
 	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
@@ -1091,7 +984,7 @@ int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, j
 		return JP_OK;
 	}
 	FwdBuffers b;
-	JP_TRY(fwd_alloc(c, nlen, b));
+	JP_TRY(fwd_alloc(c, nlen, b, d_out));                               // the output block is scratch until the emission
 	JP_TRY(suffix_sort(c, d_in, nlen, b, s, st));
 	k_fwd_emit<<<(int)(((i64)nlen + 1023) / 1024), 256, 0, s>>>(d_in, b.SA, b.ISA, nlen, d_out); JP_LAUNCH(c);
 	k_fwd_trailer<<<1, 128, 0, s>>>(d_in, b.ISA, nlen, len, d_out); JP_LAUNCH(c);
@@ -1100,7 +993,7 @@ int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, j
 	JP_CUDA(cudaStreamSynchronize(s));
 	for (int i = 0; i < 5; i++) JP_CUDA(cudaEventElapsedTime(&st->ms_phase[i], c.ev[i], c.ev[i + 1]));
 	JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[5]));
-	st->device_bytes = c.arena.high;
+	st->device_bytes = c.arena.high + c.arena2.cap;
 	return JP_OK;
 }
 
@@ -1111,9 +1004,9 @@ int debug_suffix_array(Ctx& c, const u8* h_in, i32 n, i32* h_sa)
 	c.arena.reset();
 	FwdBuffers b;
 	const size_t N = (size_t)n;
-	JP_TRY(arena_reserve(c, N * 56 + (8u << 20)));
+	JP_TRY(arena_reserve(c, Arena::align(N + 16) + fwd_bytes(n, true)));   // text + workspace in one reservation
 	u8* d_T = arena_take<u8>(c, N + 16);
-	JP_TRY(fwd_alloc(c, n, b));
+	JP_TRY(fwd_alloc(c, n, b, nullptr));
 	JP_CUDA(cudaMemcpyAsync(d_T, h_in, N, cudaMemcpyHostToDevice, s));
 	JP_CUDA(cudaEventRecord(c.ev[0], s));
 	jp_bwt_stats st = {};

@@ -6,6 +6,11 @@
 
 namespace jp {
 
+// Longest block an entry point accepts: the reference's buffers are 1.05 * MAX_BLOCKSIZE (jampack.cpp:74-76), but the
+// inverse keeps row numbers in 30 bits of an LF entry (bits 30/31 are the anchor and mark flags, bwt_inverse.cu), so a
+// block -- in either direction: what the forward emits must be invertible -- stops two rows short of 2^30.
+constexpr i64 JP_BWT_MAX_CALL_LEN = ((i64)JP_BWT_MAX_LEN * 105 / 100) < (((i64)1 << 30) - 2) ? ((i64)JP_BWT_MAX_LEN * 105 / 100) : (((i64)1 << 30) - 2);
+
 // Grow-only bump arena: one cudaMalloc per context, re-used by every call that borrows the context
 // (cudaMalloc of gigabytes costs milliseconds; a block stage is called once per block).
 struct Arena {
@@ -19,6 +24,7 @@ struct Ctx {
 	int          device = -1;
 	cudaStream_t own_stream = nullptr;
 	Arena        arena;
+	Arena        arena2;              // second, lazily grown allocation: scratch only unusual blocks need (forward: sorting over-long groups)
 	int*         h_small = nullptr;   // pinned: error flag + counters read back per round (64 ints)
 	u8*          h_stage[2] = {nullptr, nullptr}; // pinned staging for pageable host blocks
 	size_t       h_stage_cap = 0;
@@ -34,6 +40,8 @@ struct Ctx {
 
 // Reserve `total` bytes up front (re-allocating the arena if it is too small), then carve.
 int arena_reserve(Ctx& c, size_t total);
+// The second arena is used whole (no carving): at least `total` bytes at c.arena2.base afterwards.
+int arena2_reserve(Ctx& c, size_t total);
 template <typename T> inline T* arena_take(Ctx& c, size_t count)
 {
 	size_t bytes = Arena::align(count * sizeof(T));

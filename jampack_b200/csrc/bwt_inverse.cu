@@ -39,7 +39,7 @@ constexpr int  INV_CHUNK      = INV_WARPS * 512; // bytes ranked per block itera
 constexpr u32  LF_MARK        = 0x80000000u;     // row starts a sub-chain
 constexpr u32  LF_ANCHOR      = 0x40000000u;     // ... and is one of the 121 anchor rows (set together with LF_MARK)
 constexpr u32  LF_MASK        = 0x3fffffffu;     // row numbers need 30 bits: nlen <= 1000 * 2^20 < 2^30 (format.hpp:22)
-static_assert((u64)JP_BWT_MAX_LEN + 1 <= (u64)LF_MASK, "row numbers must leave bits 30 and 31 free");
+static_assert((u64)JP_BWT_MAX_CALL_LEN + 1 <= (u64)LF_MASK, "row numbers of every accepted block must leave bits 30 and 31 free");
 constexpr int  N_ANCHOR       = JP_BWT_UNITS + 1; // anchor k = row of text position k*step, k = 0..120
 constexpr u32  REC_INVALID    = 0xffffffffu;
 constexpr int  RANK_HOP_CAP   = 1 << 22;

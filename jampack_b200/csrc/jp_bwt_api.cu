@@ -87,6 +87,16 @@ int arena_reserve(Ctx& c, size_t total)
 	return JP_OK;
 }
 
+int arena2_reserve(Ctx& c, size_t total)
+{
+	if (c.arena2.cap >= total) return JP_OK;
+	if (c.arena2.base) { dev_free(c.device, c.arena2.base, c.arena2.cap); c.arena2.base = nullptr; c.arena2.cap = 0; }
+	const size_t want = (total + (16u << 20) - 1) & ~(size_t)((16u << 20) - 1);
+	JP_TRY(dev_alloc(c.device, (void**)&c.arena2.base, want));
+	c.arena2.cap = want;
+	return JP_OK;
+}
+
 // ---- optional stage trace (JP_BWT_TRACE=1): per-direction totals printed to stderr at exit ---------------
 // The reference's own progress line reports CPU time (clock(), jampack.cpp:202-229); this gives the wall-clock
 // view of just this stage when it runs inside the reference's pipeline (BASELINE.json configs[3]).
@@ -178,13 +188,14 @@ static int init_devices_locked()
 	}
 	if (g_pool.devices.empty()) for (int i = 0; i < n; i++) g_pool.devices.push_back(i);
 	g_pool.devices_ready = true;
-	g_pool.pending.assign((size_t)(n > 0 ? n : 1), 0);
-	g_pool.state.assign((size_t)(n > 0 ? n : 1), 0);
+	// (a reset while calls are in flight keeps the counts of contexts being created and the devices already up)
+	if (g_pool.pending.size() < (size_t)(n > 0 ? n : 1)) g_pool.pending.resize((size_t)(n > 0 ? n : 1), 0);
+	if (g_pool.state.size() < (size_t)(n > 0 ? n : 1)) g_pool.state.resize((size_t)(n > 0 ? n : 1), 0);
 	if (g_pool.devices.empty()) { set_error_detail("no CUDA device visible; this stage has no CPU path"); return JP_ERR_NO_DEVICE; }
 	// Only the first configured device is brought up here. A primary context costs about a second on these parts
 	// and the driver creates them one after the other (measured: first batch of a 4-GPU run waited 3-5 s), so the
 	// other devices come up in the background the first time the usable ones are saturated (warm_next_device).
-	g_pool.state[g_pool.devices[0]] = 2;
+	if (g_pool.state[g_pool.devices[0]] == 0) g_pool.state[g_pool.devices[0]] = 2;
 	return JP_OK;
 }
 
@@ -257,6 +268,15 @@ static int acquire(int device, Ctx** out)
 				for (auto& c : g_pool.ctxs) if (c->device == d && c->busy) load++;
 				if (load < best_load) { best_load = load; best = d; }
 			}
+			if (best < 0) {
+				// no configured device is usable yet: bring one up (or wait for the one on its way); none left -> fail
+				bool coming = false, cold = false;
+				for (int d : g_pool.devices) { coming |= g_pool.state[d] == 1; cold |= g_pool.state[d] == 0; }
+				if (!coming && !cold) { set_error_detail("no configured CUDA device could be brought up"); return JP_ERR_NO_DEVICE; }
+				if (!coming) warm_next_device_locked();
+				g_pool.cv.wait_for(lk, std::chrono::milliseconds(50));
+				continue;
+			}
 			device = best;
 			if (best_load < MAX_CTX_PER_DEVICE) g_pool.rr++;
 			else if (waited) warm_next_device_locked();          // every usable device has stayed full: widen the pool meanwhile
@@ -275,6 +295,7 @@ static int acquire(int device, Ctx** out)
 			const int rc = create_ctx(device, out);
 			lk.lock();
 			g_pool.pending[device]--;
+			if (rc != JP_OK && rc != JP_ERR_OOM) g_pool.state[device] = 3;   // the device itself failed: the 'any' path stops choosing it
 			lk.unlock();
 			if (rc != JP_OK) g_pool.cv.notify_all();
 			return rc;
@@ -311,6 +332,7 @@ static int ensure_io(Ctx& c, size_t bytes)
 static void drop_memory(Ctx& c)
 {
 	dev_free(c.device, c.arena.base, c.arena.cap); c.arena.base = nullptr; c.arena.cap = 0; c.arena.off = 0;
+	dev_free(c.device, c.arena2.base, c.arena2.cap); c.arena2.base = nullptr; c.arena2.cap = 0;
 	dev_free(c.device, c.d_in, c.d_io_cap); c.d_in = nullptr;
 	dev_free(c.device, c.d_out, c.d_io_cap); c.d_out = nullptr;
 	c.d_io_cap = 0;
@@ -326,7 +348,7 @@ static bool relieve_memory_pressure(Ctx& self)
 	for (auto& c : g_pool.ctxs) {
 		if (c.get() == &self || c->device != self.device) continue;
 		if (c->busy) others_busy = true;
-		else if (c->arena.base || c->d_in) { c->busy = true; idle.push_back(c.get()); }
+		else if (c->arena.base || c->arena2.base || c->d_in) { c->busy = true; idle.push_back(c.get()); }
 	}
 	if (!idle.empty()) {
 		lk.unlock();
@@ -358,7 +380,7 @@ static int host_call(int direction, const u8* in, i32 in_len, u8* out, i32* out_
 	if (!in || !out || !out_len || in_len < 0) { set_error_detail("null pointer or negative length"); return JP_ERR_ARG; }
 	if (direction == 1 && in_len < JP_BWT_TRAILER_BYTES) { set_error_detail("inverse input shorter than its trailer"); return JP_ERR_ARG; }
 	const i32 len = direction == 0 ? in_len : in_len - JP_BWT_TRAILER_BYTES;
-	if ((i64)len > (i64)JP_BWT_MAX_LEN * 105 / 100) { set_error_detail("block longer than 1.05 * MAX_BLOCKSIZE"); return JP_ERR_ARG; }
+	if ((i64)len > JP_BWT_MAX_CALL_LEN) { set_error_detail("block longer than %lld bytes", (long long)JP_BWT_MAX_CALL_LEN); return JP_ERR_ARG; }
 	const i32 nlen = len - len % JP_BWT_UNITS;
 	*out_len = direction == 0 ? len + JP_BWT_TRAILER_BYTES : len;          // bwt.cpp:27 / :78
 	const bool tr = trace_enabled();
@@ -413,6 +435,7 @@ static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int
 	if (!d_in || !d_out || in_len < 0 || device < 0) { set_error_detail("null pointer, negative length or device"); return JP_ERR_ARG; }
 	if (direction == 1 && in_len < JP_BWT_TRAILER_BYTES) { set_error_detail("inverse input shorter than its trailer"); return JP_ERR_ARG; }
 	if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) { set_error_detail("device blocks must be 16-byte aligned"); return JP_ERR_ARG; }
+	if ((i64)in_len - (direction == 1 ? JP_BWT_TRAILER_BYTES : 0) > JP_BWT_MAX_CALL_LEN) { set_error_detail("block longer than %lld bytes", (long long)JP_BWT_MAX_CALL_LEN); return JP_ERR_ARG; }
 	CtxGuard g;
 	JP_TRY(acquire(device, &g.c));
 	Ctx& c = *g.c;
@@ -501,10 +524,16 @@ int jp_bwt_debug_lf(const uint8_t* in, int32_t nlen, int32_t* lf, int32_t* ctabl
 int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
 {
 	if (n < 0 || (n > 0 && (!in || !sa))) { set_error_detail("null pointer or negative length"); return JP_ERR_ARG; }
-	if ((i64)n > (i64)JP_BWT_MAX_LEN * 105 / 100) { set_error_detail("block longer than 1.05 * MAX_BLOCKSIZE"); return JP_ERR_ARG; }
-	CtxGuard g; JP_TRY(acquire(-1, &g.c)); begin_call(*g.c);
+	if ((i64)n > JP_BWT_MAX_CALL_LEN) { set_error_detail("block longer than %lld bytes", (long long)JP_BWT_MAX_CALL_LEN); return JP_ERR_ARG; }
 	if (n == 0) return JP_OK;
-	const int rc = debug_suffix_array(*g.c, in, n, sa);
+	CtxGuard g; JP_TRY(acquire(-1, &g.c));
+	// same out-of-memory policy as the stage entry points: -m2 blocks run from the same OpenMP team (lz77.cpp:141)
+	int rc = JP_ERR_OOM;
+	for (int attempt = 0; attempt < 256 && rc == JP_ERR_OOM; attempt++) {
+		if (attempt > 0 && !relieve_memory_pressure(*g.c)) break;
+		begin_call(*g.c);
+		rc = debug_suffix_array(*g.c, in, n, sa);
+	}
 	t_stats.kernel_launches = g.c->launches;
 	t_stats.device_bytes = g.c->arena.high;
 	return rc;

@@ -29,6 +29,16 @@ int arena_reserve(Ctx& c, size_t total)
 	return c.arena.base ? JP_OK : JP_ERR_OOM;
 }
 
+int arena2_reserve(Ctx& c, size_t total)
+{
+	if (c.arena2.cap >= total) return JP_OK;
+	free(c.arena2.base);
+	c.arena2.cap = total + 4096;
+	c.arena2.base = (u8*)aligned_alloc(256, (c.arena2.cap + 255) & ~(size_t)255);
+	memset(c.arena2.base, 0xA5, c.arena2.cap);
+	return c.arena2.base ? JP_OK : JP_ERR_OOM;
+}
+
 static Ctx& ctx()
 {
 	static Ctx c;

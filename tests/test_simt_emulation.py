@@ -105,51 +105,6 @@ def test_emulated_forward(emu, orc, kind, n, seed):
         assert launches > 0
 
 
-# ---- run skip (JP_BWT_FWD_RUNSKIP=1, off by default): single-symbol runs resolved by run length instead of by doubling ----
-def _run_cases():
-    rng = np.random.default_rng(37)
-    cases = {"all_a": np.full(9000, 97, np.uint8), "tiny_all_a": np.full(360, 5, np.uint8)}
-    T = rng.integers(0, 200, 20000).astype(np.uint8); T[5000:15000] = 0
-    cases["zero_page_in_noise"] = T
-    T = np.zeros(12000, np.uint8); T[4000:] = 1; T[8000:] = 0
-    cases["three_plateaus"] = T
-    T = rng.integers(0, 4, 8000).astype(np.uint8); T[-500:] = 255; T[:300] = 255
-    cases["runs_at_both_ends"] = T
-    # two suffixes 1 0^92 2... and 1 0^92 1...: their order hangs on what follows equally long runs, read by ORDINARY
-    # suffixes through the ranks of run suffixes (the case that broke keying on ISA[v + r] regardless of h)
-    def seq(*runs):
-        return np.concatenate([np.full(l, c, np.uint8) for c, l in runs])
-    cases["equal_runs_different_followers"] = np.concatenate([
-        seq((2, 40), (1, 1), (0, 92), (2, 10), (1, 89), (0, 80), (2, 57)), seq((1, 33), (2, 5)),
-        seq((1, 1), (0, 92), (1, 76), (2, 17), (0, 47), (2, 28)), seq((0, 35), (1, 2), (0, 31), (2, 1))])
-    for k in range(4):
-        n = 2400 + 700 * k
-        cases[f"random_runs_{k}"] = np.ascontiguousarray(np.repeat(rng.integers(0, 2 + k, n // 10 + 1).astype(np.uint8),
-                                                                   rng.integers(1, 64 + 10 * k, n // 10 + 1))[:n])
-    return cases
-
-
-@pytest.mark.parametrize("name", sorted(_run_cases()))
-def test_emulated_forward_with_run_skip(emu, orc, name):
-    T = _run_cases()[name]
-    want = orc.forward(T, "port", prefill=0x5C)
-    saved = os.environ.get("JP_BWT_FWD_RUNSKIP")
-    try:
-        os.environ["JP_BWT_FWD_RUNSKIP"] = "0"
-        rc0, got0, rounds0, _ = emu.forward(T)
-        os.environ["JP_BWT_FWD_RUNSKIP"] = "1"
-        rc1, got1, rounds1, _ = emu.forward(T)
-    finally:
-        if saved is None:
-            os.environ.pop("JP_BWT_FWD_RUNSKIP", None)
-        else:
-            os.environ["JP_BWT_FWD_RUNSKIP"] = saved
-    assert rc0 == 0 and (got0 == want).all()
-    assert rc1 == 0 and (got1 == want).all()
-    if name in ("all_a", "zero_page_in_noise", "three_plateaus"):
-        assert rounds1 <= 2 < rounds0, (rounds0, rounds1)      # one pass over the runs instead of log2(run / depth) rounds
-
-
 @pytest.mark.parametrize("kind,n,seed", [("kat_extremes", 2, 0), ("uniform", 3, 1), ("alla", 1000, 0), ("markov2", 3000, 2), ("repetitive", 5000, 3)])
 def test_emulated_suffix_array(emu, orc, kind, n, seed):
     """jp::debug_suffix_array (the sorter behind jp_bwt_suffix_array / the -m2 shim) against a brute-force sort."""

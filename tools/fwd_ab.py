@@ -14,4 +14,4 @@ for i in range(5):
 fnv = "%016x" % synth.fnv(d_B.cpu().numpy())
 gold = {c["name"]: c["fnv_all"] for c in json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kat.json")))["big"]}
 ok = gold.get(f"{kind}-{mib}M") == fnv
-print(f"ENV={ {k:v for k,v in os.environ.items() if k.startswith('JP_BWT')} } {kind} {mib}MiB golden_ok={ok} total={best['ms_total']:.3f} phases={[round(x,3) for x in best['ms_phase'][:5]]} rounds={best['rounds']} global_rounds={best['ms_phase'][5]} radix_tiles={best['ms_phase'][6]} a={best['active_fraction']} bytes={best['device_bytes']} -> {n/best['ms_total']/1e6:.2f} GB/s")
+print(f"ENV={ {k:v for k,v in os.environ.items() if k.startswith('JP_BWT')} } {kind} {mib}MiB golden_ok={ok} total={best['ms_total']:.3f} phases={[round(x,3) for x in best['ms_phase'][:5]]} rounds={best['rounds']} large={best['large_fraction']:.3f} radix_tiles={best['radix_tiles']} bypass={best['bypass_suffixes']}/{best['bypass_runs']} period={best['period']} a={best['active_fraction']} ws={best['device_bytes']/n:.2f}N -> {n/best['ms_total']/1e6:.2f} GB/s")

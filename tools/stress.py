@@ -47,7 +47,7 @@ for c in range(cases):
     back = jp.inverse(want)
     chunks = jp.last_stats().stream_chunks      # > 0: single-walk inverse (JP_BWT_INV_SINGLE=1 forces it on these sizes)
     ok_i = bool((back == T).all())
-    print(f"case {c:3d} kind={kind} n={n:9d} sigma={np.unique(T).size:3d} rounds={fs.rounds:2d} fwd={fs.ms_total:8.2f} ms large={fs.ms_phase[5]:.3f} "
+    print(f"case {c:3d} kind={kind} n={n:9d} sigma={np.unique(T).size:3d} rounds={fs.rounds:2d} fwd={fs.ms_total:8.2f} ms large={fs.large_fraction:.3f} "
           f"forward={'ok' if ok_f else 'MISMATCH'} inverse={'ok' if ok_i else 'MISMATCH'} stream_chunks={chunks}", flush=True)
     bad += (not ok_f) + (not ok_i)
 print(f"STRESS {cases} cases, {bad} failures, {time.time() - t0:.0f} s")
