@@ -26,6 +26,7 @@
 #include "radix_sort.cuh"
 #include <algorithm>
 #include <chrono>
+#include <vector>
 
 namespace jp {
 
@@ -35,8 +36,8 @@ constexpr u32 AP_POS  = 0x3fffffffu;     // ... and its position in SA (blocks s
 struct FwdMeta {
 	u32 code[256];
 	i32 sigma, bits, depth, key_bits;   // bits: per symbol (reported); depth: symbols per key; key_bits: bit length of the largest key
-	u32 hist[256];
 	u32 eq4;                            // aligned 4-byte words of one repeated byte: a cheap screen for single-symbol runs
+	u32 hist[256];
 };
 
 // ---- 1. symbol histogram and dense codes -------------------------------------------------------------
@@ -96,11 +97,17 @@ __global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
 // ---- 2. initial keys -------------------------------------------------------------------------------
 // One block builds the keys of one radix tile (RS_TILE positions) and, having them in hand, also counts the
 // lowest digit: the first radix pass starts from this tile histogram instead of re-reading the keys.
+// COMPACT (run bypass, below): positions whose bit is set in `skip` get no key; the others are written back to back, tile
+// t starting at skip_base[t] -- the output tiles no longer coincide with the input tiles, so no histogram is produced.
 constexpr int KEY_TILE = RS_TILE;
+template <bool COMPACT>
 __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 n, const FwdMeta* __restrict__ meta,
                                                   u64* __restrict__ keys, u32* __restrict__ vals,
-                                                  u32* __restrict__ tile_hist, u32 stride)
+                                                  u32* __restrict__ tile_hist, u32 stride,
+                                                  const u32* __restrict__ skip, const u32* __restrict__ skip_base)
 {
+	__shared__ u32 sword[KEY_TILE / 32], wpre[KEY_TILE / 32];
+	__shared__ u32 ws[32];
 	__shared__ u16 sc[KEY_TILE + 64];
 	__shared__ u32 part[KEY_TILE + 32];       // value of the q = depth/2 symbols starting at each position (fits 32 bits)
 	__shared__ u16 code[256];
@@ -126,6 +133,20 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 	}
 	u64 hi_scale = 1;
 	for (int d = 0; d < depth - q; d++) hi_scale *= radix;
+	u32 out_base = 0;
+	if (COMPACT) {
+		u32 keep = 0;                                  // positions of word t that get a key
+		if (t < KEY_TILE / 32) {
+			const i64 p0 = base + (i64)t * 32;
+			const u32 valid = p0 + 32 <= n ? 0xffffffffu : (p0 < n ? (1u << (u32)(n - p0)) - 1u : 0u);
+			const u32 wd = p0 < n ? skip[p0 >> 5] : 0u;
+			sword[t] = keep = ~wd & valid;
+		}
+		u32 total;
+		const u32 inc = block_incl_sum((u32)__popc(keep), ws, &total);
+		if (t < KEY_TILE / 32) wpre[t] = inc - (u32)__popc(keep);
+		out_base = skip_base[blockIdx.x];
+	}
 	__syncthreads();
 	#pragma unroll 4
 	for (int j = 0; j < KEY_TILE / 256; j++) {
@@ -135,16 +156,299 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 			u64 tail = part[li + q];
 			if (depth & 1) tail = tail * radix + sc[li + 2 * q];
 			const u64 k = (u64)part[li] * hi_scale + tail;
-			keys[p] = k;
-			vals[p] = (u32)p;
-			atomicAdd(&h[w][(u32)k & 255u], 1u);           // low digits of text-order keys are spread: lanes rarely collide
+			if (COMPACT) {
+				const u32 wd = sword[li >> 5], bit = 1u << (li & 31);
+				if (wd & bit) { const u32 o = out_base + wpre[li >> 5] + (u32)__popc(wd & (bit - 1u)); keys[o] = k; vals[o] = (u32)p; }
+			} else {
+				keys[p] = k;
+				vals[p] = (u32)p;
+				atomicAdd(&h[w][(u32)k & 255u], 1u);       // low digits of text-order keys are spread: lanes rarely collide
+			}
 		}
 	}
+	if (COMPACT) return;
 	__syncthreads();
 	u32 sum = 0;
 	#pragma unroll
 	for (int k = 0; k < 8; k++) sum += h[k][t];
 	tile_hist[(size_t)t * stride + blockIdx.x] = sum;
+}
+
+
+// ---- 2b. single-symbol runs: placed, not sorted ("run bypass") -------------------------------------------
+// Prefix doubling pays one round per doubling of the longest repeat, and the cheapest way to make a long repeat is a
+// run of one symbol (zero pages, padding, fill bytes): a block of n equal bytes costs log2(n / depth) rounds over the
+// whole block. Runs have an exact shortcut. Let r(v) be the length of the run of T[v] that starts at v, and call v a
+// RUN SUFFIX when r(v) >= depth, the number of symbols in the initial key: its key is c^depth, so the run suffixes of a
+// symbol c are exactly the initial group of that key, and inside it suffix v = c^r(v) X(v), where X(v) starts with a
+// symbol other than c (or is empty). Comparing c^r X with c^r' X', r < r', is decided at position r: X's first symbol
+// against c. Hence the order inside the group is: first the suffixes whose run is followed by a SMALLER symbol (or by
+// the end of the text), by ascending r; then those followed by a larger one, by descending r; ties -- equal class and
+// r: they come from different runs -- by the order of the X's.
+// So run suffixes never enter the initial sort. A maximal run of length L >= depth contributes the suffixes r = depth..L
+// of its (symbol, class) BUCKET; level r of a bucket holds one suffix of every run of the bucket with L >= r. With the
+// bucket's runs listed by descending L (a sort of the RUNS, of which there are few), a run's index in that list is its
+// index inside every level it reaches, and the first position of level r is a prefix sum over the list:
+//     offset(r) = sum over runs with L < r of (L - depth + 1)  +  #{L >= r} * (r - depth).
+// Every run suffix therefore computes its own position in SA; the sorted non-run suffixes are laid around the buckets
+// (a bucket sits where its key c^depth would sort); levels with one member are final at once, the others are ordinary
+// groups that the doubling rounds refine by what follows the runs. A block of one repeated byte is finished without a
+// single round.
+constexpr int RUN_TILE = KEY_TILE;
+constexpr u32 RUN_NONE = 0xffffffffu;
+constexpr u32 RUN_MAXL = (1u << 30) - 1;
+
+struct RunTabs {
+	u32* bits;                  // bit v: suffix v is a run suffix                                    (n/32 + 2 words)
+	u32* tile_first; u32* tile_next;   // per tile of RUN_TILE positions: run-end bookkeeping of the detection
+	u32* tile_base;             // per tile: run suffixes in it; after the scan: non-run suffixes before it
+	u32* run_s; u32* run_L;     // runs of length >= depth, in no particular order                        (cap entries)
+	u64* rk[2]; u32* rv[2];     // (bucket, descending length) sort of the runs
+	u32* PS;                    // exclusive prefix sums of (L - depth + 1) over the sorted runs; PS[R] = all run suffixes
+	u32* bstart; u32* bend;     // sorted-run range of each bucket                                       (512 each)
+	u32* lo;                    // first SA position of each bucket                                        (512)
+	u64* shift_key; u32* shift_cum;   // run key of each symbol code, run suffixes of the codes below it   (256 / 257)
+	u32* counters;              // [0] runs seen [1] run suffixes [2] run suffixes whose level holds more than one run
+	u32 cap;
+};
+
+__device__ __forceinline__ u32 warp_min_u32(u32 v)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// The same three kernels serve repeats of any period p (see "periodic repeats" further down): position j BREAKS the
+// period when T[j] != T[j + p] or j + p >= n; for p = 1 that is the last position of a run.
+__device__ __forceinline__ bool per_break(const u8* __restrict__ T, u32 n, u32 p, u32 j) { return j + p >= n || T[j] != T[j + p]; }
+
+// first break inside the tile; RUN_NONE if there is none
+__global__ void __launch_bounds__(256) k_run_first(const u8* __restrict__ T, u32 n, u32 p, u32* __restrict__ tile_first)
+{
+	__shared__ u32 wbest[8];
+	const u32 base = blockIdx.x * RUN_TILE;
+	u32 best = RUN_NONE;
+	#pragma unroll 4
+	for (int i = 0; i < RUN_TILE / 256; i++) {
+		const u32 j = base + i * 256 + threadIdx.x;
+		if (j < n && per_break(T, n, p, j)) best = min(best, j);
+	}
+	best = warp_min_u32(best);
+	if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		#pragma unroll
+		for (int k = 1; k < 8; k++) best = min(best, wbest[k]);
+		tile_first[blockIdx.x] = best;
+	}
+}
+
+// single block: tile_next[t] = first run end in any LATER tile (exclusive suffix minimum)
+__global__ void __launch_bounds__(1024) k_run_scan(const u32* __restrict__ tile_first, u32 tiles, u32* __restrict__ tile_next)
+{
+	__shared__ u32 part[1024];
+	const u32 t = threadIdx.x;
+	const u32 per = (tiles + 1023) / 1024;
+	const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	u32 m = RUN_NONE;
+	for (u32 k = lo; k < hi; k++) m = min(m, tile_first[k]);
+	part[t] = m;
+	__syncthreads();
+	u32 run = RUN_NONE;
+	for (u32 k = t + 1; k < 1024; k++) run = min(run, part[k]);
+	for (u32 k = hi; k > lo; k--) { tile_next[k - 1] = run; run = min(run, tile_first[k - 1]); }
+}
+
+// r(j) = (first break at or after j) - j + p = length of the p-periodic stretch that starts at j; bits = (r(j) >= thr).
+// LIST (run bypass, p = 1): the runs of length >= thr that START in the tile are appended to the run list; tile_base[tile] =
+// run suffixes in the tile; counters[0] += runs, counters[1] += run suffixes. Otherwise (periodic repeats): RL[j] = r(j).
+template <bool LIST>
+__global__ void __launch_bounds__(256) k_run_fill(const u8* __restrict__ T, u32 n, u32 p, const u32* __restrict__ tile_next, u32 thr, RunTabs rt,
+                                                  u32* __restrict__ RL)
+{
+	__shared__ u32 end_at[RUN_TILE];            // last position of the run each position of the tile lies in
+	__shared__ u32 wfirst[8];
+	__shared__ u32 s_cnt;
+	constexpr int PER = RUN_TILE / 256;
+	const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const u32 base = blockIdx.x * RUN_TILE;
+	if (t == 0) s_cnt = 0;
+	// each thread owns PER consecutive positions: its first run end, if any
+	u32 mine = RUN_NONE;
+	#pragma unroll 4
+	for (int k = PER - 1; k >= 0; k--) {
+		const u32 j = base + t * PER + k;
+		if (j < n && per_break(T, n, p, j)) mine = j;
+	}
+	// exclusive suffix minimum over the threads: inside the warp by shuffles, across the 8 warps through shared memory
+	u32 incl = mine;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl = min(incl, x); }
+	u32 excl = __shfl_down_sync(0xffffffffu, incl, 1);
+	if (lane == 31) excl = RUN_NONE;
+	if (lane == 0) wfirst[w] = incl;
+	__syncthreads();
+	u32 carry = min(tile_next[blockIdx.x], excl);
+	for (u32 k = 7; k > w; k--) carry = min(carry, wfirst[k]);
+	#pragma unroll 4
+	for (int k = PER - 1; k >= 0; k--) {
+		const u32 j = base + t * PER + k;
+		if (j < n && per_break(T, n, p, j)) carry = j;
+		end_at[t * PER + k] = carry;
+	}
+	__syncthreads();
+	u32 cnt = 0;
+	#pragma unroll 4
+	for (int i = 0; i < PER; i++) {
+		const u32 j = base + i * 256 + t;
+		u32 r = 0;
+		if (j < n) r = end_at[i * 256 + t] - j + p;
+		const bool rs = j < n && r >= thr;
+		const u32 m = __ballot_sync(0xffffffffu, rs);
+		if (lane == 0 && base + i * 256 + (t & ~31u) < n) { rt.bits[(base + i * 256 + t) >> 5] = m; cnt += __popc(m); }
+		if (LIST) {
+			if (rs && (j == 0 || T[j - 1] != T[j])) {         // a run of length >= thr starts here
+				const u32 k = atomicAdd(&rt.counters[0], 1u);
+				if (k < rt.cap) { rt.run_s[k] = j; rt.run_L[k] = r; }
+			}
+		} else if (j < n) RL[j] = r;
+	}
+	if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+	__syncthreads();
+	if (t == 0) { if (LIST) rt.tile_base[blockIdx.x] = s_cnt; if (s_cnt) atomicAdd(&rt.counters[1], s_cnt); }
+}
+
+// single block: tile_base[t] <- number of NON-run suffixes in the tiles before t
+__global__ void __launch_bounds__(1024) k_run_tile_scan(u32* __restrict__ tile_base, u32 tiles, u32 n)
+{
+	__shared__ u32 ws[32];
+	const u32 t = threadIdx.x;
+	const u32 per = (tiles + 1023) / 1024;
+	const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
+	u32 s = 0;
+	for (u32 k = lo; k < hi; k++) s += min((u32)RUN_TILE, n - k * RUN_TILE) - tile_base[k];
+	u32 total;
+	u32 run = block_incl_sum(s, ws, &total) - s;
+	for (u32 k = lo; k < hi; k++) { const u32 c = min((u32)RUN_TILE, n - k * RUN_TILE) - tile_base[k]; tile_base[k] = run; run += c; }
+}
+
+// sort key of a run: (bucket = 2 * (code - 1) + class, descending length)
+__global__ void __launch_bounds__(256) k_run_keys(const u8* __restrict__ T, u32 n, const FwdMeta* __restrict__ meta, RunTabs rt, u32 R)
+{
+	const u32 k = blockIdx.x * 256 + threadIdx.x;
+	if (k >= R) return;
+	const u32 s = rt.run_s[k], L = rt.run_L[k], e = s + L;
+	const u32 c = T[s];
+	const u32 cls = (e >= n || T[e] < c) ? 0u : 1u;          // what follows the run: smaller (or the end of the text) / larger
+	const u32 b = (meta->code[c] - 1u) * 2u + cls;
+	rt.rk[0][k] = ((u64)b << 30) | (u64)(RUN_MAXL - L);
+	rt.rv[0][k] = k;
+}
+
+// single block over the sorted runs: PS, bucket ranges
+__global__ void __launch_bounds__(1024) k_run_tables(const u64* __restrict__ sk, u32 R, u32 depth, RunTabs rt)
+{
+	__shared__ u32 ws[32];
+	const u32 t = threadIdx.x;
+	if (t < 512) { rt.bstart[t] = R; rt.bend[t] = 0; }
+	__syncthreads();
+	const u32 per = (R + 1023) / 1024;
+	const u32 lo = min(R, t * per), hi = min(R, lo + per);
+	u32 s = 0;
+	for (u32 i = lo; i < hi; i++) s += (RUN_MAXL - (u32)(sk[i] & RUN_MAXL)) - depth + 1;
+	u32 total;
+	u32 run = block_incl_sum(s, ws, &total) - s;
+	for (u32 i = lo; i < hi; i++) {
+		const u64 key = sk[i];
+		const u32 b = (u32)(key >> 30);
+		rt.PS[i] = run;
+		run += (RUN_MAXL - (u32)(key & RUN_MAXL)) - depth + 1;
+		if (i == 0 || (u32)(sk[i - 1] >> 30) != b) rt.bstart[b] = i;
+		if (i + 1 == R || (u32)(sk[i + 1] >> 30) != b) rt.bend[b] = i + 1;
+	}
+	if (t == 1023) rt.PS[R] = total;
+}
+
+// one thread per symbol code: where its bucket pair sits in SA, and the shift table of the non-run suffixes
+__global__ void __launch_bounds__(256) k_run_lo(const u64* __restrict__ K, u32 n_sorted, const FwdMeta* __restrict__ meta, RunTabs rt)
+{
+	__shared__ u32 ws[32];
+	const u32 c = threadIdx.x;                       // code - 1
+	const u32 sigma = (u32)meta->sigma, depth = (u32)meta->depth;
+	const u64 radix = (u64)sigma + 1;
+	u64 rep = 0;                                     // 1 + radix + ... + radix^(depth-1): the key of code 1 repeated
+	for (u32 d = 0; d < depth; d++) rep = rep * radix + 1;
+	u32 m0 = 0, m1 = 0, less = 0;
+	u64 rkey = ~0ull;
+	if (c < sigma) {
+		rkey = rep * (u64)(c + 1);
+		const u32 b0 = 2 * c, b1 = 2 * c + 1;
+		if (rt.bend[b0] > rt.bstart[b0]) m0 = rt.PS[rt.bend[b0]] - rt.PS[rt.bstart[b0]];
+		if (rt.bend[b1] > rt.bstart[b1]) m1 = rt.PS[rt.bend[b1]] - rt.PS[rt.bstart[b1]];
+		u32 lo = 0, hi = n_sorted;                   // first sorted key >= rkey
+		while (lo < hi) { const u32 mid = lo + ((hi - lo) >> 1); if (K[mid] < rkey) lo = mid + 1; else hi = mid; }
+		less = lo;
+	}
+	u32 total;
+	const u32 cum = block_incl_sum(m0 + m1, ws, &total) - (m0 + m1);
+	rt.shift_key[c] = rkey;
+	rt.shift_cum[c + 1] = cum + m0 + m1;
+	if (c == 0) rt.shift_cum[0] = 0;
+	if (c < sigma) { rt.lo[2 * c] = less + cum; rt.lo[2 * c + 1] = less + cum + m0; }
+}
+
+// the sorted non-run suffixes take their places around the buckets; head flags from the key changes
+__global__ void __launch_bounds__(256) k_place_sorted(const u64* __restrict__ K, const u32* __restrict__ V, u32 n_sorted, RunTabs rt,
+                                                      u32* __restrict__ SA, u8* __restrict__ F)
+{
+	__shared__ u64 skey[256];
+	__shared__ u32 scum[257];
+	const u32 t = threadIdx.x;
+	skey[t] = rt.shift_key[t];
+	scum[t] = rt.shift_cum[t];
+	if (t == 0) scum[256] = rt.shift_cum[256];
+	__syncthreads();
+	const u32 j = blockIdx.x * 256 + t;
+	if (j >= n_sorted) return;
+	const u64 k = K[j];
+	u32 lo = 0;                                       // number of run keys below k (none equals it)
+	#pragma unroll
+	for (u32 st = 128; st > 0; st >>= 1) if (skey[lo + st - 1] < k) lo += st;
+	if (lo == 255 && skey[255] < k) lo = 256;
+	const u32 pos = j + scum[lo];
+	SA[pos] = V[j];
+	F[pos] = (j == 0 || K[j - 1] != k) ? 1 : 0;
+}
+
+// every run suffix computes its own place
+__global__ void __launch_bounds__(256) k_place_runs(const u64* __restrict__ sk, const u32* __restrict__ sv, u32 R, u32 M, u32 depth, RunTabs rt,
+                                                    u32* __restrict__ SA, u8* __restrict__ F)
+{
+	const u32 u = blockIdx.x * 256 + threadIdx.x;
+	u32 q = 0;
+	if (u < M) {
+		u32 lo = 0, hi = R;                            // last run i with PS[i] <= u
+		while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (rt.PS[mid] <= u) lo = mid; else hi = mid; }
+		const u32 i = lo, toff = u - rt.PS[i];
+		const u64 key = sk[i];
+		const u32 b = (u32)(key >> 30), L = RUN_MAXL - (u32)(key & RUN_MAXL);
+		const u32 r = L - toff, v = rt.run_s[sv[i]] + toff;
+		const u32 bs = rt.bstart[b], be = rt.bend[b];
+		// q = runs of the bucket that reach level r = sorted keys in [bs, be) not above (b, r)
+		const u64 lim = ((u64)b << 30) | (u64)(RUN_MAXL - r);
+		u32 a = bs, z = be;
+		while (a < z) { const u32 mid = a + ((z - a) >> 1); if (sk[mid] <= lim) a = mid + 1; else z = mid; }
+		q = a - bs;
+		const u32 idx = i - bs;
+		const u32 off = (rt.PS[be] - rt.PS[bs + q]) + q * (r - depth);
+		const u32 Mb = rt.PS[be] - rt.PS[bs];
+		const u32 pos = (b & 1u) == 0 ? rt.lo[b] + off + idx : rt.lo[b] + Mb - off - q + idx;
+		SA[pos] = v;
+		F[pos] = idx == 0 ? 1 : 0;
+	}
+	const u32 shared = __popc(__ballot_sync(0xffffffffu, q > 1));     // run suffixes in levels that several runs reach
+	if (shared && (threadIdx.x & 31) == 0) atomicAdd(&rt.counters[2], shared);
 }
 
 // ---- 4. group heads -> ranks, retire singletons, compact the rest -------------------------------------
@@ -347,6 +651,55 @@ __device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restric
 	u32 p = v + h;
 	if (p > n) { dev_fail(err, DE_FWD_RANGE); p = n; }
 	return __ldg(&ISA[p]);
+}
+
+// ---- 5p. periodic repeats --------------------------------------------------------------------------------
+// The run argument holds for any period p. Let r(v) be the length of the longest p-periodic string that starts at v
+// (T[v + i] = T[v + i + p] for i < r(v) - p). Two suffixes v, v' that share their first p symbols and have r(v) < r(v')
+// agree on r(v) symbols and differ at offset r(v), where v breaks the period and v' does not: their order is the order
+// of T[v + r] against T[v + r - p], v's own symbols. So once the groups are h-groups with h >= p, the members of a group
+// with r >= h -- a property of the shared h symbols, hence of the whole group or of none of it -- are ordered by
+// (break goes down: ascending r | break goes up: descending r), ties by the rank of the suffix at v + r. In key2_of:
+//   * pass A (one round, h unchanged): a flagged suffix (bit set: r(v) >= the h of this round) takes key2 = r, or 2n+1-r;
+//   * pass B (the same h again) and every later round: a flagged suffix with r(v) >= h takes ISA[v + r(v)], any other
+//     suffix the ordinary ISA[v + h]. Either way the key is uniform inside a group (its members have the same r) and the
+//     round leaves every suffix at least 2h-ordered, which is what the ordinary keys of the next round rely on.
+// A text of period p with sparse defects (the `repetitive` generator of BASELINE configs[2]: p = 1021, one flipped bit
+// every 64 Ki) then needs log2(p / depth) ordinary rounds plus these two instead of log2(64 Ki / depth).
+// The period is not searched for in the text: after a stable sort the members of a group are in text order, so in a
+// periodic text the distance between neighbours of a group IS the period. A sample of those distances is histogrammed
+// after the initial step; the mode, if it covers most of the block, is p.
+constexpr u32 PER_MAXP = 65536;
+constexpr u32 PER_SAMPLE = 64;
+__global__ void __launch_bounds__(256) k_per_sample(const u32* __restrict__ AP, const u32* __restrict__ SA, u32 A, u32* __restrict__ hist)
+{
+	const u32 j = (blockIdx.x * 256 + threadIdx.x) * PER_SAMPLE;
+	u32 d = 0;
+	if (j + 1 < A && !(AP[j + 1] & AP_HEAD)) {
+		const u32 a = SA[AP[j] & AP_POS], b = SA[AP[j + 1] & AP_POS];
+		if (b > a && b - a < PER_MAXP) d = b - a;
+	}
+	const u32 peers = __match_any_sync(0xffffffffu, d);
+	if (d && (peers & lanemask_lt()) == 0) atomicAdd(&hist[d], (u32)__popc(peers));
+}
+// single block: out[0] = most frequent distance, out[1] = its count
+__global__ void __launch_bounds__(1024) k_per_pick(const u32* __restrict__ hist, u32* __restrict__ out)
+{
+	__shared__ u32 sc[32], sd[32];
+	const u32 t = threadIdx.x;
+	u32 best = 0, bd = 0;
+	for (u32 d = 1 + t; d < PER_MAXP; d += 1024) { const u32 c = hist[d]; if (c > best) { best = c; bd = d; } }
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const u32 oc = __shfl_xor_sync(0xffffffffu, best, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
+		if (oc > best || (oc == best && od < bd)) { best = oc; bd = od; }
+	}
+	if ((t & 31) == 0) { sc[t >> 5] = best; sd[t >> 5] = bd; }
+	__syncthreads();
+	if (t == 0) {
+		for (int k = 1; k < 32; k++) if (sc[k] > best || (sc[k] == best && sd[k] < bd)) { best = sc[k]; bd = sd[k]; }
+		out[0] = bd; out[1] = best;
+	}
 }
 
 // ---- 5a. small groups: gather + segmented sort in shared memory -----------------------------------------
@@ -672,32 +1025,33 @@ __device__ __forceinline__ u32 large_group_of(const u32* __restrict__ lg_off, u3
 	return lo;
 }
 
+// (a batch = the large groups g0.. whose suffixes are numbers x0 .. x0 + count of the back-to-back layout)
 template <bool PS>
 __global__ void __launch_bounds__(256) k_large_extract(const u32* __restrict__ AP, const u32* __restrict__ SA, const u32* __restrict__ ISA, u32 h, u32 n, int rank_bits,
-                                                       const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 ng, u32 total,
+                                                       const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 ng, u32 g0, u32 x0, u32 count,
                                                        u64* __restrict__ LK, u32* __restrict__ LV, int* __restrict__ err, PerSkip ps)
 {
 	const u32 x = blockIdx.x * 256 + threadIdx.x;
-	if (x >= total) return;
-	const u32 g = large_group_of(lg_off, ng, x);
-	const u32 v = SA[AP[lg_head[g] + (x - lg_off[g])] & AP_POS];
+	if (x >= count) return;
+	const u32 g = large_group_of(lg_off, ng, x0 + x);
+	const u32 v = SA[AP[lg_head[g] + (x0 + x - lg_off[g])] & AP_POS];
 	const u32 k2 = key2_of<PS>(v, h, n, ISA, ps, err);
-	LK[x] = ((u64)g << rank_bits) | (u64)k2;
+	LK[x] = ((u64)(g - g0) << rank_bits) | (u64)k2;
 	LV[x] = v;
 }
 
 __global__ void __launch_bounds__(256) k_large_writeback(const u64* __restrict__ LK, const u32* __restrict__ LV, int rank_bits,
-                                                         const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 total,
+                                                         const u32* __restrict__ lg_head, const u32* __restrict__ lg_off, u32 g0, u32 x0, u32 count,
                                                          const u32* __restrict__ AP, u32* __restrict__ SA, u8* __restrict__ F)
 {
 	const u32 x = blockIdx.x * 256 + threadIdx.x;
-	if (x >= total) return;
+	if (x >= count) return;
 	const u64 k = LK[x];
-	const u32 g = (u32)(k >> rank_bits);
+	const u32 g = g0 + (u32)(k >> rank_bits);
 	const u32 o = lg_off[g];
-	const u32 slot = lg_head[g] + (x - o);
+	const u32 slot = lg_head[g] + (x0 + x - o);
 	SA[AP[slot] & AP_POS] = LV[x];
-	F[slot] = (x == o || LK[x - 1] != k) ? 1 : 0;
+	F[slot] = (x0 + x == o || LK[x - 1] != k) ? 1 : 0;
 }
 
 // ---- 6. emission ---------------------------------------------------------------------------------------
@@ -846,6 +1200,28 @@ static int group_step(Ctx& c, FwdBuffers& b, const u32* APin, u32* APout, u32 A,
 	return JP_OK;
 }
 
+// The run bypass keeps its tables in the second arena (only blocks that pass the screen pay for them).
+static int run_tabs_alloc(Ctx& c, i32 n, u32 tiles, RunTabs& rt)
+{
+	const size_t N = (size_t)n;
+	rt.cap = (u32)std::max<size_t>(4096, N / 256);
+	const size_t cap = rt.cap;
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
+	const size_t o_bits = take((N / 32 + 2) * 4), o_tf = take((size_t)tiles * 4), o_tn = take((size_t)tiles * 4), o_tb = take((size_t)tiles * 4),
+	             o_rs = take(cap * 4), o_rl = take(cap * 4), o_k0 = take(cap * 8), o_k1 = take(cap * 8), o_v0 = take(cap * 4), o_v1 = take(cap * 4),
+	             o_ps = take((cap + 1) * 4), o_bs = take(512 * 4), o_be = take(512 * 4), o_lo = take(512 * 4), o_sk = take(256 * 8),
+	             o_sc = take(257 * 4), o_ct = take(64);
+	JP_TRY(arena2_reserve(c, off));
+	u8* a = c.arena2.base;
+	rt.bits = (u32*)(a + o_bits); rt.tile_first = (u32*)(a + o_tf); rt.tile_next = (u32*)(a + o_tn); rt.tile_base = (u32*)(a + o_tb);
+	rt.run_s = (u32*)(a + o_rs); rt.run_L = (u32*)(a + o_rl);
+	rt.rk[0] = (u64*)(a + o_k0); rt.rk[1] = (u64*)(a + o_k1); rt.rv[0] = (u32*)(a + o_v0); rt.rv[1] = (u32*)(a + o_v1);
+	rt.PS = (u32*)(a + o_ps); rt.bstart = (u32*)(a + o_bs); rt.bend = (u32*)(a + o_be); rt.lo = (u32*)(a + o_lo);
+	rt.shift_key = (u64*)(a + o_sk); rt.shift_cum = (u32*)(a + o_sc); rt.counters = (u32*)(a + o_ct);
+	return JP_OK;
+}
+
 // Builds SA and ISA (ranks 1..n; ISA[n] = 0) of T[0..n) in b. Events ev[1..4] mark the phase boundaries.
 static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t s, jp_bwt_stats* st)
 {
@@ -857,46 +1233,158 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_symhist<<<hblocks, 256, 0, s>>>(d_T, n, b.meta); JP_LAUNCH(c);
 	k_fwd_codes<<<1, 256, 0, s>>>(b.meta); JP_LAUNCH(c);
 	JP_KCHECK();
-	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 4 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth, key_bits
+	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 5 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth, key_bits, eq4
 	JP_CUDA(cudaStreamSynchronize(s));
 	const int bits = c.h_small[17], depth = c.h_small[18], key_bits0 = c.h_small[19];
 	if (bits < 1 || bits > 9 || depth < 7 || depth > 63 || key_bits0 < 1 || key_bits0 > 63) { set_error_detail("symbol remap gave bits=%d depth=%d key bits=%d", bits, depth, key_bits0); return JP_ERR_INTERNAL; }
 	st->symbol_bits = bits; st->initial_depth = depth;
 
-	k_fwd_keys<<<(n + KEY_TILE - 1) / KEY_TILE, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
-	                                                         rs_stride((u32)radix_tiles((size_t)n))); JP_LAUNCH(c);
+	// Run bypass: worth its detection pass when a visible share of the block sits in single-symbol runs (the histogram
+	// kernel counted aligned words of one repeated byte); JP_BWT_FWD_BYPASS=0/1 overrides the screen.
+	RunTabs rt = {};
+	u32 R = 0, M = 0;
+	bool bypass = (u64)(u32)c.h_small[20] * 4 * 32 >= (u64)n;
+	if (const char* e = getenv("JP_BWT_FWD_BYPASS")) bypass = atoi(e) != 0;
+	const u32 ktiles = (u32)(((size_t)n + KEY_TILE - 1) / KEY_TILE);
+	if (bypass) {
+		JP_TRY(run_tabs_alloc(c, n, ktiles, rt));
+		JP_CUDA(cudaMemsetAsync(rt.counters, 0, 64, s));
+		k_run_first<<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, rt.tile_first); JP_LAUNCH(c);
+		k_run_scan<<<1, 1024, 0, s>>>(rt.tile_first, ktiles, rt.tile_next); JP_LAUNCH(c);
+		k_run_fill<true><<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, rt.tile_next, (u32)depth, rt, nullptr); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaMemcpyAsync(c.h_small + 14, rt.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+		JP_CUDA(cudaStreamSynchronize(s));
+		R = (u32)c.h_small[14]; M = (u32)c.h_small[15];
+		if (R == 0 || R > rt.cap) bypass = false;          // nothing to place, or more runs than the tables hold: plain doubling
+	}
+	const u32 n_sorted = bypass ? (u32)n - M : (u32)n;
+	if (bypass) {
+		st->bypass_suffixes = (i32)M; st->bypass_runs = (i32)R;
+		k_run_tile_scan<<<1, 1024, 0, s>>>(rt.tile_base, ktiles, (u32)n); JP_LAUNCH(c);
+		k_fwd_keys<true><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], nullptr, 0, rt.bits, rt.tile_base); JP_LAUNCH(c);
+	} else {
+		k_fwd_keys<false><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
+		                                         rs_stride((u32)radix_tiles((size_t)n)), nullptr, nullptr); JP_LAUNCH(c);
+	}
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[1], s));
 	if (cudaFuncSetAttribute(k_seg_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_seg_sort_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
-	const int cur = radix_sort_pairs(b.rb, 0, (u32)n, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/true);
+	const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
 	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 	JP_KCHECK();
 	JP_CUDA(cudaEventRecord(c.ev[2], s));
 
-	// The sorted suffix ids are the suffix array from here on; the key buffers and the other id buffer take new roles
-	// (the keys are read one last time, for the head flags).
-	b.SA = b.rb.v[cur];
-	k_fwd_flags<<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+	// The key buffers and the id buffers take new roles from here on (the keys are read one last time, for the head flags).
 	b.ISA = reinterpret_cast<u32*>(b.unit[cur ? 0 : 2]);      // first half of the other key buffer
 	b.X = reinterpret_cast<u32*>(b.unit[cur ? 1 : 3]);        // ... and its second half
 	b.AP[0] = reinterpret_cast<u32*>(b.unit[cur ? 2 : 0]);    // the sorted keys' own buffer, dead once the flags exist
 	b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
-	b.VS = b.rb.v[cur ^ 1];
+	if (!bypass) {
+		// the sorted suffix ids ARE the suffix array
+		b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
+		k_fwd_flags<<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+	} else {
+		// the suffix array is assembled in the other id buffer: sorted suffixes around the buckets, run suffixes inside them
+		b.SA = b.rb.v[cur ^ 1]; b.VS = b.rb.v[cur];
+		RadixBuffers lb = b.rb;
+		lb.k[0] = rt.rk[0]; lb.k[1] = rt.rk[1]; lb.v[0] = rt.rv[0]; lb.v[1] = rt.rv[1]; lb.dnext = nullptr;
+		k_run_keys<<<(R + 255) / 256, 256, 0, s>>>(d_T, (u32)n, b.meta, rt, R); JP_LAUNCH(c);
+		const int rc = radix_sort_pairs(lb, 0, R, 0, 30 + 9, s, &c.launches);
+		if (rc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+		k_run_tables<<<1, 1024, 0, s>>>(lb.k[rc], R, (u32)depth, rt); JP_LAUNCH(c);
+		k_run_lo<<<1, 256, 0, s>>>(b.rb.k[cur], n_sorted, b.meta, rt); JP_LAUNCH(c);
+		k_place_sorted<<<(n_sorted + 255) / 256, 256, 0, s>>>(b.rb.k[cur], b.rb.v[cur], n_sorted, rt, b.SA, b.F); JP_LAUNCH(c);
+		k_place_runs<<<(M + 255) / 256, 256, 0, s>>>(lb.k[rc], lb.v[rc], R, M, (u32)depth, rt, b.SA, b.F); JP_LAUNCH(c);
+		JP_KCHECK();
+		JP_CUDA(cudaMemcpyAsync(c.h_small + 21, rt.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
+	}
 	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
-	const int rank_bits = bit_length((u64)n);                           // key2 is a rank <= n
+	int rank_bits = bit_length((u64)n);                                 // key2 is a rank <= n (a repeat-length key <= 2n + 1)
 	JP_TRY(group_step(c, b, nullptr, b.AP[0], (u32)n, s));
-	PerSkip ps; ps.rl = nullptr; ps.bits = nullptr; ps.T = d_T; ps.p = 1; ps.first = 0;
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	int act = 0;
 	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
 	u64 sectors = 2ull * (u64)n;
 	i64 h = depth;
 	int rounds = 0;
+
+	// Periodic repeats: when most of the block is still unsorted, look for a dominant distance between group neighbours.
+	PerSkip ps; ps.rl = nullptr; ps.bits = nullptr; ps.T = d_T; ps.p = 1; ps.first = 0;
+	bool periodic = false;
+	int pass = 0;                                                       // 0: pass A still to come, 1: pass B next (same h), 2: both done
+	i64 h_a = 0;                                                        // the h of pass A: first h >= p
+	size_t keep2 = 0;                                                   // bytes at the start of the second arena that later growth must keep
+	const u32 shared_levels = bypass ? (u32)c.h_small[21] : 0;
+	bool run_jumps = shared_levels >= 2048;                              // worth a second detection pass
+	if (const char* e = getenv("JP_BWT_FWD_RUNJUMP")) run_jumps = atoi(e) != 0 && shared_levels > 0;
+	{
+		bool look = (u64)A * 4 >= (u64)n * 3 && n >= (1 << 16);
+		if (const char* e = getenv("JP_BWT_FWD_PERIODIC")) look = atoi(e) != 0 && A >= 2 * PER_SAMPLE;
+		if (look) {
+			size_t off = 0;
+			auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
+			const size_t o_bits = take(((size_t)n / 32 + 2) * 4), o_tf = take((size_t)ktiles * 4), o_tn = take((size_t)ktiles * 4), o_rl = take((size_t)n * 4),
+			             o_hist = take((size_t)PER_MAXP * 4), o_ct = take(64);
+			JP_TRY(arena2_reserve(c, off));                               // (the run bypass tables, if any, are dead by now)
+			u8* a2 = c.arena2.base;
+			u32* hist = (u32*)(a2 + o_hist); u32* ct = (u32*)(a2 + o_ct);
+			JP_CUDA(cudaMemsetAsync(hist, 0, (size_t)PER_MAXP * 4 + 64, s));
+			const u32 samples = (A + PER_SAMPLE - 1) / PER_SAMPLE;
+			k_per_sample<<<(samples + 255) / 256, 256, 0, s>>>(b.AP[0], b.SA, A, hist); JP_LAUNCH(c);
+			k_per_pick<<<1, 1024, 0, s>>>(hist, ct + 2); JP_LAUNCH(c);
+			JP_KCHECK();
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 14, ct + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaStreamSynchronize(s));
+			const u32 p = (u32)c.h_small[14], hits = (u32)c.h_small[15];
+			h_a = depth;
+			while (h_a < (i64)p) h_a *= 2;
+			if (p >= 1 && (u64)hits * PER_SAMPLE * 2 >= (u64)A && h_a * 4 <= (i64)n) {
+				periodic = true;
+				RunTabs pt = {};
+				pt.bits = (u32*)(a2 + o_bits); pt.tile_first = (u32*)(a2 + o_tf); pt.tile_next = (u32*)(a2 + o_tn); pt.counters = ct;
+				u32* RL = (u32*)(a2 + o_rl);
+				k_run_first<<<ktiles, 256, 0, s>>>(d_T, (u32)n, p, pt.tile_first); JP_LAUNCH(c);
+				k_run_scan<<<1, 1024, 0, s>>>(pt.tile_first, ktiles, pt.tile_next); JP_LAUNCH(c);
+				k_run_fill<false><<<ktiles, 256, 0, s>>>(d_T, (u32)n, p, pt.tile_next, (u32)h_a, pt, RL); JP_LAUNCH(c);
+				JP_KCHECK();
+				ps.rl = RL; ps.bits = pt.bits; ps.p = p;
+				keep2 = o_hist;                                           // bits, tile tables and RL stay; the histogram is dead
+				rank_bits = bit_length(2 * (u64)n + 1);
+				st->period = (i32)p;
+			}
+		}
+	}
+	if (!periodic && A > 0 && run_jumps) {
+		// Run bypass left levels that several runs of equal symbol and class reach (padding to a fixed record size, say):
+		// ordinary groups, but ones whose members differ only in what follows their runs. They are already uniform in
+		// (class, run length) -- the placement did what pass A does -- so the jump keys of pass B apply from the first round on:
+		// a run suffix with r >= h takes the rank of the suffix right after its run, and such a level is resolved as soon
+		// as the followers differ instead of after log2(run length / depth) rounds.
+		size_t off = 0;
+		auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
+		const size_t o_bits = take(((size_t)n / 32 + 2) * 4), o_tf = take((size_t)ktiles * 4), o_tn = take((size_t)ktiles * 4), o_rl = take((size_t)n * 4), o_ct = take(64);
+		JP_TRY(arena2_reserve(c, off));                                   // (the bypass tables are dead: everything is placed)
+		u8* a2 = c.arena2.base;
+		RunTabs pt = {};
+		pt.bits = (u32*)(a2 + o_bits); pt.tile_first = (u32*)(a2 + o_tf); pt.tile_next = (u32*)(a2 + o_tn); pt.counters = (u32*)(a2 + o_ct);
+		u32* RL = (u32*)(a2 + o_rl);
+		JP_CUDA(cudaMemsetAsync(pt.counters, 0, 64, s));
+		k_run_first<<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, pt.tile_first); JP_LAUNCH(c);
+		k_run_scan<<<1, 1024, 0, s>>>(pt.tile_first, ktiles, pt.tile_next); JP_LAUNCH(c);
+		k_run_fill<false><<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, pt.tile_next, (u32)depth, pt, RL); JP_LAUNCH(c);
+		JP_KCHECK();
+		ps.rl = RL; ps.bits = pt.bits; ps.p = 1;
+		periodic = true; pass = 1; h_a = depth;
+		keep2 = o_ct;
+		st->period = 1;
+	}
 	const bool trace_rounds = getenv("JP_BWT_TRACE_ROUNDS") != nullptr;      // one stderr line per doubling round (host wall time)
 	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	std::vector<u32> h_off;
 	while (A > 0) {
 		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
 		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
@@ -904,11 +1392,14 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		sectors += 2ull * A;
 		double large_frac_now = 0.0;
 		const u32* AP = b.AP[act];
+		const bool use_ps = periodic && h >= h_a;                        // the repeat-length keys apply from the first h >= p on
+		ps.first = (use_ps && pass == 0) ? 1u : 0u;
 		// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
 		// shared-memory radix kernel; groups longer than a window are reported for the large-group route
 		const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
 		JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
-		k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
+		if (use_ps) k_seg_sort<true><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
+		else k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -916,7 +1407,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		const bool large = c.h_small[10] != 0;
 		const u32 queued = (u32)c.h_small[11];
 		if (queued) {
-			k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
+			if (use_ps) k_seg_sort_radix<true><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
+			else k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
 			JP_LAUNCH(c);
 			JP_KCHECK();
 			st->radix_tiles += (i32)queued;
@@ -930,38 +1422,57 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			st->large_fraction += (float)((double)total / (double)n);   // share of the block on the large-group route, summed over rounds
 			large_frac_now = (double)total / (double)A;
 			if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
-			// scratch of the sort: the spare unit, the staging unit and the idle active buffer hold (8 + 8 + 2 x 4) bytes for
-			// up to N/2 suffixes; beyond that (blocks that are mostly long repeats) the second arena provides
-			RadixBuffers lb = b.rb;
-			lb.dnext = nullptr;                             // the flag bytes of this round are live in b.F
-			if ((size_t)total * 8 <= b.usz) {
-				lb.k[0] = reinterpret_cast<u64*>(b.X); lb.k[1] = reinterpret_cast<u64*>(b.VS);
-				lb.v[0] = b.AP[act ^ 1]; lb.v[1] = b.AP[act ^ 1] + b.usz / 8;
-			} else {
-				const size_t T8 = Arena::align((size_t)total * 8), T4 = Arena::align((size_t)total * 4);
-				JP_TRY(arena2_reserve(c, 2 * T8 + 2 * T4));
-				lb.k[0] = reinterpret_cast<u64*>(c.arena2.base); lb.k[1] = reinterpret_cast<u64*>(c.arena2.base + T8);
-				lb.v[0] = reinterpret_cast<u32*>(c.arena2.base + 2 * T8); lb.v[1] = reinterpret_cast<u32*>(c.arena2.base + 2 * T8 + T4);
+			// Scratch of the sort: the spare unit, the staging unit and the idle active buffer hold (8 + 8 + 2 x 4) bytes for
+			// up to N/2 suffixes. More than that (blocks that are mostly long repeats) goes through in batches of whole groups;
+			// a single group beyond N/2 falls back on the second arena.
+			const u32 cap = (u32)(b.usz / 8);
+			if (total > cap) {
+				h_off.resize((size_t)ng + 1);
+				JP_CUDA(cudaMemcpyAsync(h_off.data(), b.lg_off, ((size_t)ng + 1) * 4, cudaMemcpyDeviceToHost, s));
+				JP_CUDA(cudaStreamSynchronize(s));
 			}
-			k_large_extract<false><<<(total + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, total,
-			                                                    lb.k[0], lb.v[0], b.err, ps);
-			JP_LAUNCH(c);
-			const int key_bits = rank_bits + bit_length((u64)(ng - 1));
-			const int lc = radix_sort_pairs(lb, 0, total, 0, key_bits, s, &c.launches);
-			if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-			k_large_writeback<<<(total + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, total, AP, b.SA, b.F); JP_LAUNCH(c);
-			JP_KCHECK();
+			for (u32 g0 = 0; g0 < ng;) {
+				u32 g1 = ng, x0 = 0, count = total;
+				if (total > cap) {
+					g1 = g0 + 1;
+					while (g1 < ng && h_off[g1 + 1] - h_off[g0] <= cap) g1++;
+					x0 = h_off[g0]; count = h_off[g1] - x0;
+				}
+				RadixBuffers lb = b.rb;
+				lb.dnext = nullptr;                         // the flag bytes of this round are live in b.F
+				if (count <= cap) {
+					lb.k[0] = reinterpret_cast<u64*>(b.X); lb.k[1] = reinterpret_cast<u64*>(b.VS);
+					lb.v[0] = b.AP[act ^ 1]; lb.v[1] = b.AP[act ^ 1] + b.usz / 8;
+				} else {
+					const size_t T8 = Arena::align((size_t)count * 8), T4 = Arena::align((size_t)count * 4), base = Arena::align(keep2);
+					JP_TRY(arena2_reserve(c, base + 2 * T8 + 2 * T4, keep2));
+					u8* a2 = c.arena2.base;
+					if (periodic) { ps.bits = (const u32*)a2; ps.rl = (const u32*)(a2 + ((const u8*)ps.rl - (const u8*)ps.bits)); }
+					lb.k[0] = reinterpret_cast<u64*>(a2 + base); lb.k[1] = reinterpret_cast<u64*>(a2 + base + T8);
+					lb.v[0] = reinterpret_cast<u32*>(a2 + base + 2 * T8); lb.v[1] = reinterpret_cast<u32*>(a2 + base + 2 * T8 + T4);
+				}
+				if (use_ps) k_large_extract<true><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
+				else k_large_extract<false><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
+				JP_LAUNCH(c);
+				const int key_bits = rank_bits + bit_length((u64)(g1 - g0 - 1));
+				const int lc = radix_sort_pairs(lb, 0, count, 0, key_bits, s, &c.launches);
+				if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+				k_large_writeback<<<(count + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, g0, x0, count, AP, b.SA, b.F); JP_LAUNCH(c);
+				JP_KCHECK();
+				g0 = g1;
+			}
 		}
 		JP_TRY(group_step(c, b, AP, b.AP[act ^ 1], A, s));
 		if (trace_rounds) {
 			const double t1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-			fprintf(stderr, "[jp_bwt round] %d h=%lld active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h, A, G,
-			        (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
+			fprintf(stderr, "[jp_bwt round] %d h=%lld%s active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h,
+			        use_ps ? (pass == 0 ? " (repeat lengths)" : " (repeat jumps)") : "", A, G, (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
 			t_round = t1;
 		}
 		act ^= 1;
 		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
-		h *= 2;
+		if (use_ps && pass == 0) pass = 1;                               // pass B repeats this h
+		else { h *= 2; if (use_ps) pass = 2; }
 		rounds++;
 	}
 	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
@@ -993,7 +1504,7 @@ int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, j
 	JP_CUDA(cudaStreamSynchronize(s));
 	for (int i = 0; i < 5; i++) JP_CUDA(cudaEventElapsedTime(&st->ms_phase[i], c.ev[i], c.ev[i + 1]));
 	JP_CUDA(cudaEventElapsedTime(&st->ms_total, c.ev[0], c.ev[5]));
-	st->device_bytes = c.arena.high + c.arena2.cap;
+	st->device_bytes = c.arena.high + c.arena2.high;
 	return JP_OK;
 }
 

@@ -40,8 +40,9 @@ struct Ctx {
 
 // Reserve `total` bytes up front (re-allocating the arena if it is too small), then carve.
 int arena_reserve(Ctx& c, size_t total);
-// The second arena is used whole (no carving): at least `total` bytes at c.arena2.base afterwards.
-int arena2_reserve(Ctx& c, size_t total);
+// The second arena is used whole (no carving): at least `total` bytes at c.arena2.base afterwards. If it has to grow,
+// its first `keep` bytes are carried over (the base pointer changes).
+int arena2_reserve(Ctx& c, size_t total, size_t keep = 0);
 template <typename T> inline T* arena_take(Ctx& c, size_t count)
 {
 	size_t bytes = Arena::align(count * sizeof(T));

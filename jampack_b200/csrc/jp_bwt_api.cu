@@ -87,12 +87,20 @@ int arena_reserve(Ctx& c, size_t total)
 	return JP_OK;
 }
 
-int arena2_reserve(Ctx& c, size_t total)
+int arena2_reserve(Ctx& c, size_t total, size_t keep)
 {
+	if (total > c.arena2.high) c.arena2.high = total;      // bytes of it this call uses (reported with the workspace)
 	if (c.arena2.cap >= total) return JP_OK;
-	if (c.arena2.base) { dev_free(c.device, c.arena2.base, c.arena2.cap); c.arena2.base = nullptr; c.arena2.cap = 0; }
 	const size_t want = (total + (16u << 20) - 1) & ~(size_t)((16u << 20) - 1);
-	JP_TRY(dev_alloc(c.device, (void**)&c.arena2.base, want));
+	u8* fresh = nullptr;
+	if (keep == 0 && c.arena2.base) { dev_free(c.device, c.arena2.base, c.arena2.cap); c.arena2.base = nullptr; c.arena2.cap = 0; }
+	JP_TRY(dev_alloc(c.device, (void**)&fresh, want));
+	if (c.arena2.base) {
+		const cudaError_t e = cudaMemcpy(fresh, c.arena2.base, keep, cudaMemcpyDeviceToDevice);   // (synchronous: every stream of the call is idle here or ordered before it)
+		dev_free(c.device, c.arena2.base, c.arena2.cap);
+		if (e != cudaSuccess) { dev_free(c.device, fresh, want); c.arena2.base = nullptr; c.arena2.cap = 0; set_error_detail("arena2 carry-over: %s", cudaGetErrorString(e)); return JP_ERR_CUDA; }
+	}
+	c.arena2.base = fresh;
 	c.arena2.cap = want;
 	return JP_OK;
 }
@@ -369,6 +377,7 @@ static void begin_call(Ctx& c)
 	c.launches = 0;
 	c.arena.reset();
 	c.arena.high = 0;
+	c.arena2.high = 0;
 	memset(&t_stats, 0, sizeof(t_stats));
 	t_detail[0] = 0;
 }
@@ -426,7 +435,7 @@ static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 l
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_h2d, c.ev[8], c.ev[9]));
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
 	t_stats.kernel_launches = c.launches;
-	t_stats.device_bytes = c.arena.high;
+	t_stats.device_bytes = c.arena.high + c.arena2.high;
 	return JP_OK;
 }
 
@@ -448,7 +457,7 @@ static int device_call(int direction, const u8* d_in, i32 in_len, u8* d_out, int
 		                    : inverse_device(c, d_in, in_len, d_out, s, &t_stats, consume_in ? const_cast<u8*>(d_in) : nullptr);
 	}
 	t_stats.kernel_launches = c.launches;
-	t_stats.device_bytes = c.arena.high;
+	t_stats.device_bytes = c.arena.high + c.arena2.high;
 	return rc;
 }
 
@@ -535,7 +544,7 @@ int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
 		rc = debug_suffix_array(*g.c, in, n, sa);
 	}
 	t_stats.kernel_launches = g.c->launches;
-	t_stats.device_bytes = g.c->arena.high;
+	t_stats.device_bytes = g.c->arena.high + g.c->arena2.high;
 	return rc;
 }
 double jp_bwt_debug_gather_rate(uint64_t table_bytes, int32_t chains, int32_t steps, int dependent)

@@ -29,14 +29,18 @@ int arena_reserve(Ctx& c, size_t total)
 	return c.arena.base ? JP_OK : JP_ERR_OOM;
 }
 
-int arena2_reserve(Ctx& c, size_t total)
+int arena2_reserve(Ctx& c, size_t total, size_t keep)
 {
+	if (total > c.arena2.high) c.arena2.high = total;
 	if (c.arena2.cap >= total) return JP_OK;
+	const size_t cap = total + 4096;
+	u8* fresh = (u8*)aligned_alloc(256, (cap + 255) & ~(size_t)255);
+	if (!fresh) return JP_ERR_OOM;
+	memset(fresh, 0xA5, cap);
+	if (c.arena2.base && keep) memcpy(fresh, c.arena2.base, keep);
 	free(c.arena2.base);
-	c.arena2.cap = total + 4096;
-	c.arena2.base = (u8*)aligned_alloc(256, (c.arena2.cap + 255) & ~(size_t)255);
-	memset(c.arena2.base, 0xA5, c.arena2.cap);
-	return c.arena2.base ? JP_OK : JP_ERR_OOM;
+	c.arena2.base = fresh; c.arena2.cap = cap;
+	return JP_OK;
 }
 
 static Ctx& ctx()

@@ -537,3 +537,66 @@ def test_single_walk_rejects_corrupt_input(jp, orc, single_walk_env):
             errors += 1
     assert time.time() - t0 < 60 and errors > 0
     assert (jp.inverse(B) == T).all() and jp.last_stats().stream_chunks > 0
+
+
+@pytest.mark.parametrize("kind,n,seed", [("alla", MiB, 0), ("alla", 360, 0), ("repetitive", MiB, 3), ("markov2", MiB + 77, 1),
+                                         ("zero_pages", 3 * MiB, 5), ("runs", 2 * MiB, 6), ("tar_like", 4 * MiB, 7), ("alla", 40 * MiB, 0)])
+@pytest.mark.parametrize("force", [None, "1"])
+def test_forward_run_bypass_is_bit_exact(jp, orc, kind, n, seed, force):
+    """Suffixes inside single-symbol runs are placed by counting instead of being sorted (bwt_forward.cu, "run bypass"):
+    with the screen deciding (default) and forced on, against the compiled reference."""
+    rng = np.random.default_rng(seed)
+    if kind == "zero_pages":
+        T = rng.integers(0, 256, n).astype(np.uint8)
+        for _ in range(12):
+            a = int(rng.integers(0, n)); T[a:a + int(rng.integers(1, 1 << 17))] = 0
+    elif kind == "runs":
+        T = np.ascontiguousarray(np.repeat(rng.integers(0, 5, n // 20 + 1).astype(np.uint8), rng.integers(1, 200, n // 20 + 1))[:n])
+    elif kind == "tar_like":           # text files padded with zeros to 512-byte records: many runs of equal length
+        T = orc.gen("markov2", n, seed)
+        for a in range(0, n - 512, 512 * 7):
+            T[a + 300 + (a // 512) % 150: a + 512] = 0
+    else:
+        T = orc.gen(kind, n, seed)
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    saved = os.environ.get("JP_BWT_FWD_BYPASS")
+    if force is not None:
+        os.environ["JP_BWT_FWD_BYPASS"] = force
+    try:
+        got = jp.forward(T, prefill=0x5C)
+        st = jp.last_stats()
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_BYPASS", None)
+        else:
+            os.environ["JP_BWT_FWD_BYPASS"] = saved
+    assert (got == want).all()
+    if kind == "alla" and n >= MiB:
+        assert st.rounds == 0 and st.bypass_runs == 1 and st.bypass_suffixes > n - 200
+        assert (jp.inverse(got) == T).all()
+
+
+@pytest.mark.parametrize("kind,n,seed", [("repetitive", 4 * MiB, 3), ("repetitive", 24 * MiB + 5, 9), ("period_12", 3 * MiB, 2), ("period_5000", 6 * MiB, 4),
+                                         ("period_2_clean", 2 * MiB, 0), ("runs_in_a_period", 2 * MiB, 1), ("markov2", 2 * MiB, 1)])
+def test_forward_periodic_repeats_are_bit_exact(jp, orc, kind, n, seed):
+    """Blocks of period p with sparse defects: the repeat-length keys (bwt_forward.cu, "periodic repeats") against the
+    compiled reference, with the detection deciding on its own."""
+    rng = np.random.default_rng(seed)
+    if kind.startswith("period_"):
+        p = int(kind.split("_")[1])
+        T = np.tile(rng.integers(0, 4, p).astype(np.uint8) + 97, n // p + 1)[:n].copy()
+        if not kind.endswith("clean"):
+            T[rng.integers(0, n, 40)] ^= 1
+    elif kind == "runs_in_a_period":
+        T = np.tile(np.concatenate([np.zeros(700, np.uint8), np.array([1, 2, 1], np.uint8)]), n // 703 + 1)[:n].copy()
+        T[rng.integers(0, n, 9)] = 5
+    else:
+        T = orc.gen(kind, n, seed)
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    got = jp.forward(T, prefill=0x5C)
+    st = jp.last_stats()
+    assert (got == want).all()
+    if kind == "repetitive":
+        assert st.period == 1021 and st.rounds <= 10, (st.period, st.rounds)
+    if kind == "markov2":
+        assert st.period == 0

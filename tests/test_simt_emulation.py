@@ -105,6 +105,97 @@ def test_emulated_forward(emu, orc, kind, n, seed):
         assert launches > 0
 
 
+# ---- run bypass: suffixes inside single-symbol runs are placed by counting instead of being sorted ----
+def _run_cases():
+    rng = np.random.default_rng(37)
+    cases = {"all_a": np.full(9000, 97, np.uint8), "tiny_all_a": np.full(360, 5, np.uint8)}
+    T = rng.integers(0, 200, 20000).astype(np.uint8); T[5000:15000] = 0
+    cases["zero_page_in_noise"] = T
+    T = np.zeros(12000, np.uint8); T[4000:] = 1; T[8000:] = 0
+    cases["three_plateaus"] = T
+    T = rng.integers(0, 4, 8000).astype(np.uint8); T[-500:] = 255; T[:300] = 255
+    cases["runs_at_both_ends"] = T
+    # two suffixes 1 0^92 2... and 1 0^92 1...: their order hangs on what follows equally long runs
+    def seq(*runs):
+        return np.concatenate([np.full(l, c, np.uint8) for c, l in runs])
+    cases["equal_runs_different_followers"] = np.concatenate([
+        seq((2, 40), (1, 1), (0, 92), (2, 10), (1, 89), (0, 80), (2, 57)), seq((1, 33), (2, 5)),
+        seq((1, 1), (0, 92), (1, 76), (2, 17), (0, 47), (2, 28)), seq((0, 35), (1, 2), (0, 31), (2, 1))])
+    for k in range(4):
+        n = 2400 + 700 * k
+        cases[f"random_runs_{k}"] = np.ascontiguousarray(np.repeat(rng.integers(0, 2 + k, n // 10 + 1).astype(np.uint8),
+                                                                   rng.integers(1, 64 + 10 * k, n // 10 + 1))[:n])
+    # 256 symbols (the largest alphabet, base 257 keys), runs of the extreme byte values, equal runs back to back
+    T = rng.integers(0, 256, 9000).astype(np.uint8); T[100:400] = 255; T[1000:1300] = 0; T[2000:2300] = 255; T[-64:] = 0
+    cases["extreme_bytes_256_symbols"] = T
+    cases["many_equal_runs"] = np.tile(np.concatenate([np.zeros(70, np.uint8), np.array([1, 2, 1], np.uint8)]), 60)
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_run_cases()))
+def test_emulated_forward_with_run_bypass(emu, orc, name):
+    T = _run_cases()[name]
+    want = orc.forward(T, "port", prefill=0x5C)
+    saved = os.environ.get("JP_BWT_FWD_BYPASS")
+    try:
+        os.environ["JP_BWT_FWD_BYPASS"] = "0"
+        rc0, got0, rounds0, _ = emu.forward(T)
+        os.environ["JP_BWT_FWD_BYPASS"] = "1"
+        rc1, got1, rounds1, _ = emu.forward(T)
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_BYPASS", None)
+        else:
+            os.environ["JP_BWT_FWD_BYPASS"] = saved
+    assert rc0 == 0 and (got0 == want).all()
+    assert rc1 == 0 and (got1 == want).all()
+    if name in ("all_a", "tiny_all_a"):
+        assert rounds1 == 0 < rounds0, (rounds0, rounds1)      # a block of one repeated byte needs no doubling round at all
+    if name in ("zero_page_in_noise", "three_plateaus"):
+        assert rounds1 < rounds0, (rounds0, rounds1)
+
+
+def _periodic(n, p, sig, defects, seed):
+    r = np.random.default_rng(seed)
+    T = np.tile(r.integers(0, sig, p).astype(np.uint8), n // p + 1)[:n].copy()
+    for d in r.integers(0, n, defects):
+        T[d] ^= 1
+    return T
+
+
+PERIODIC_CASES = {"repetitive_70k": lambda orc: orc.gen("repetitive", 70000, 3), "period_3": lambda orc: _periodic(30000, 3, 4, 5, 1),
+                  "period_7_clean": lambda orc: _periodic(50000, 7, 3, 0, 2), "period_60": lambda orc: _periodic(40000, 60, 5, 10, 3),
+                  "period_300_binary": lambda orc: _periodic(90000, 300, 2, 4, 4), "period_2": lambda orc: _periodic(20000, 2, 2, 3, 6),
+                  "runs_in_a_period": lambda orc: np.tile(np.concatenate([np.zeros(70, np.uint8), np.array([1, 2, 1], np.uint8)]), 200),
+                  "not_periodic": lambda orc: orc.gen("markov2", 30000, 1)}
+
+
+@pytest.mark.parametrize("name", sorted(PERIODIC_CASES))
+def test_emulated_forward_with_periodic_repeats(emu, orc, name):
+    """Repeats of period p ordered by repeat length (bwt_forward.cu, "periodic repeats"), alone and on top of the run bypass
+    and its jump keys; the detection is forced on (blocks under 64 Ki do not look for a period by default)."""
+    T = PERIODIC_CASES[name](orc)
+    want = orc.forward(T, "port", prefill=0x5C)
+    keys = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP")
+    saved = {k: os.environ.get(k) for k in keys}
+    rounds = {}
+    try:
+        for bp, per in (("0", "0"), ("0", "1"), ("1", "1")):
+            os.environ["JP_BWT_FWD_BYPASS"] = bp
+            os.environ["JP_BWT_FWD_PERIODIC"] = per
+            os.environ["JP_BWT_FWD_RUNJUMP"] = bp
+            rc, got, rounds[bp + per], _ = emu.forward(T)
+            assert rc == 0 and (got == want).all(), (bp, per)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if name.startswith(("repetitive", "period_")):
+        assert rounds["01"] < rounds["00"], rounds
+
+
 @pytest.mark.parametrize("kind,n,seed", [("kat_extremes", 2, 0), ("uniform", 3, 1), ("alla", 1000, 0), ("markov2", 3000, 2), ("repetitive", 5000, 3)])
 def test_emulated_suffix_array(emu, orc, kind, n, seed):
     """jp::debug_suffix_array (the sorter behind jp_bwt_suffix_array / the -m2 shim) against a brute-force sort."""

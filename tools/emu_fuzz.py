@@ -1,7 +1,7 @@
 """Differential fuzzing of the product's kernel code under the SIMT emulator (tests/simt) against the oracle: random
 structured blocks (noise over 1..256 symbols, runs, periodic data with defects, near-constant blocks, order-2 text,
-copy-paste text, plateaus) through the forward (JP_BWT_FWD_RUNSKIP off and on) and through every inverse variant
-(two-pass, single-walk, four sub-chains per thread, four nodes per thread in the ranking). CPU only, test infrastructure.
+copy-paste text, plateaus) through the forward (run bypass forced off and on, rank staging forced on) and through both
+inverse paths (two-pass, single-walk). CPU only, test infrastructure.
     python tools/emu_fuzz.py [cases] [seed]"""
 import os
 import sys
@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 import oracle  # noqa: E402
 import simt  # noqa: E402
 
-SWITCHES = ("JP_BWT_FWD_RUNSKIP", "JP_BWT_INV_SINGLE", "JP_BWT_INV_ILP", "JP_BWT_INV_RANK_ILP", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM")
+SWITCHES = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2", "JP_BWT_INV_SINGLE", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM")
 
 
 def block(rng, n):
@@ -56,16 +56,17 @@ def main():
         T = block(rng, int(rng.integers(66000, 150000)) if big else int(rng.integers(121, 7000)))
         want = oracle.forward(T, "port", prefill=0x5C)
         if not big:                                        # the forward is slow under emulation: small blocks only
-            for rs in ("0", "1"):
-                os.environ["JP_BWT_FWD_RUNSKIP"] = rs
+            for fv in ({"JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PERIODIC": "0"}, {"JP_BWT_FWD_BYPASS": "1", "JP_BWT_FWD_RUNJUMP": "1"}, {"JP_BWT_FWD_PERIODIC": "1"},
+                       {"JP_BWT_FWD_BYPASS": "1", "JP_BWT_FWD_PERIODIC": "1", "JP_BWT_ISA_STAGE_MIN": "100", "JP_BWT_ISA_REGION_LOG2": str(6 + c % 5)}):
+                for k in SWITCHES:
+                    os.environ.pop(k, None)
+                os.environ.update(fv)
                 rc, got, _, _ = simt.forward(T)
                 if rc != 0 or not (got == want).all():
-                    fails += 1; print(f"case {c}: forward mismatch (run skip {rs}) n={T.size} rc={rc}", flush=True)
+                    fails += 1; print(f"case {c}: forward mismatch {fv} n={T.size} rc={rc}", flush=True)
         variants = [{}]
         if big:
-            variants += [{"JP_BWT_INV_SINGLE": "1"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_LOG2M": "4", "JP_BWT_INV_RANK_ILP": "4"},
-                         {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_ILP": "4"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_ILP": "4", "JP_BWT_INV_LOG2M": "4",
-                                                                       "JP_BWT_INV_WBLOCKS_PER_SM": "1", "JP_BWT_INV_RANK_ILP": "4"}]
+            variants += [{"JP_BWT_INV_SINGLE": "1"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_LOG2M": "4"}]
         for v in variants:
             for k in SWITCHES:
                 os.environ.pop(k, None)
