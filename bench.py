@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configs (forward on uniform / repetitive / all-a, 256 MiB block, 8 MiB CPU round trip)")
     ap.add_argument("--callers", type=int, default=4, help="blocks in flight per GPU (the library keeps up to JP_BWT_MAX_CTX=4 contexts per device)")
     return ap.parse_args()
 
@@ -229,6 +230,70 @@ def workload_config(args, n):
             "l2": "per-block working set 6N = %d MB %s the 126 MB L2; no explicit flush" % (6 * n // 10**6, "exceeds" if 6 * n > 126e6 else "fits in")}
 
 
+# ---- the other BASELINE.json configs, one line each (N = 1 only) -----------------------------------------------
+def other_configs(jp, synth, torch, dev, with_cpu):
+    """configs[2]: forward of 64 MiB uniform / repetitive / all-a blocks (and their inverse); configs[4]: one 256 MiB block,
+    forward + inverse with the workspace each direction holds; configs[0]: the reference CLI's 8 MiB CPU round trip.
+    One block at a time, resident in HBM, best of 3 warm runs; the CPU figure beside each is the unmodified reference,
+    one block per host core (jampack.cpp:215-219 shape), one batch."""
+    gold = {}
+    try:
+        for c in json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json"))).get("big", []):
+            gold[(c["kind"], c["len"], c["seed"])] = c["fnv_all"]
+    except Exception:  # noqa: BLE001
+        pass
+    cores = os.cpu_count() or 1
+    rows = []
+    for kind, mib, seed, cfg in (("uniform", 64, 2, "configs[2]"), ("repetitive", 64, 3, "configs[2]"), ("alla", 64, 0, "configs[2]"), ("markov2", 256, 5, "configs[4]")):
+        n = mib * MiB
+        T = synth.gen(kind, n, seed)
+        d_T = torch.from_numpy(T).to(dev)
+        d_B = torch.zeros(n + TRAILER, dtype=torch.uint8, device=dev)
+        d_back = torch.zeros(n, dtype=torch.uint8, device=dev)
+        bf = bi = None
+        for _ in range(4):
+            jp.forward_device(d_T, d_B); s = jp.last_stats().asdict()
+            if bf is None or s["ms_total"] < bf["ms_total"]:
+                bf = s
+        B = d_B.cpu().numpy()
+        for _ in range(4):
+            jp.inverse_device(d_B, d_back); s = jp.last_stats().asdict()
+            if bi is None or s["ms_total"] < bi["ms_total"]:
+                bi = s
+        row = {"config": cfg, "input": f"{kind}({mib} MiB, seed {seed})", "forward_MBps": round(n / bf["ms_total"] / 1e3, 1), "forward_ms": round(bf["ms_total"], 3),
+               "rounds": bf["rounds"], "sum_active_fraction": round(sum(bf["active_fraction"]), 4), "initial_depth": bf["initial_depth"],
+               "run_bypass_suffixes": bf["bypass_suffixes"], "period": bf["period"],
+               "forward_workspace_bytes_per_byte": round(bf["device_bytes"] / n, 2), "forward_phases_ms": bf["ms_phase"][:5],
+               "inverse_MBps": round(n / bi["ms_total"] / 1e3, 1), "inverse_ms": round(bi["ms_total"], 3),
+               "inverse_workspace_bytes_per_byte": round(bi["device_bytes"] / n, 3),
+               "round_trip": bool(torch.equal(d_back, d_T)),
+               "forward_matches_reference_hash": (("%016x" % synth.fnv(B)) == gold[(kind, n, seed)]) if (kind, n, seed) in gold else None}
+        del d_T, d_B, d_back
+        if with_cpu and mib <= 64:
+            cf = cpu_reference("forward", T, B, cores)
+            ci = cpu_reference("inverse", T, B, cores)
+            row["cpu_baseline"] = {"forward_MBps": cf["value"], "inverse_MBps": ci["value"], "cores": cores, "kind": cf["kind"], "sample": cf["sample"],
+                                   "output_matches": bool(cf["output_matches"] and ci["output_matches"])}
+            row["forward_x_cpu"] = round(row["forward_MBps"] / cf["value"], 1)
+            row["inverse_x_cpu"] = round(row["inverse_MBps"] / ci["value"], 1)
+        rows.append(row)
+    out = {"blocks": rows}
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "Jampack_ref")
+    if with_cpu and os.path.isfile(ref_cli):
+        import hashlib
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            src, jam, back = os.path.join(d, "in"), os.path.join(d, "out.jam"), os.path.join(d, "back")
+            synth.gen("markov2", 8 * MiB, 1).tofile(src)
+            t0 = time.perf_counter(); subprocess.run([ref_cli, "c", src, jam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False); tc = time.perf_counter() - t0
+            t0 = time.perf_counter(); subprocess.run([ref_cli, "d", jam, back], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False); td = time.perf_counter() - t0
+            sha = lambda p: hashlib.sha256(open(p, "rb").read()).hexdigest() if os.path.isfile(p) else None  # noqa: E731
+            out["config0_cpu_round_trip"] = {"input": "markov2(8 MiB, seed 1)", "command": "Jampack_ref c / d, default settings (reference main.cpp)",
+                                             "compress_s": round(tc, 2), "decompress_s": round(td, 2), "jam_bytes": os.path.getsize(jam) if os.path.isfile(jam) else None,
+                                             "jam_sha256": sha(jam), "round_trip": sha(back) == sha(src), "threads": cores}
+    return out
+
+
 # ---- our arm ----------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -349,6 +414,62 @@ def main():
             hi.free(); ho.free()
         return ms, ok
 
+    # The same callers doing ONLY the copies of those calls (jp_bwt_debug_copy: pinned block -> device, device -> pinned
+    # block, no kernels): what the host side of this box allows, i.e. the ceiling of the end-to-end figure.
+    def timed_copy_ceiling(direction, callers):
+        nin, nout = (n + TRAILER, n) if direction == "inverse" else (n, n + TRAILER)
+        bufs = [(jp.PinnedBlock(nin), jp.PinnedBlock(nout)) for _ in range(callers)]
+
+        def worker(i, reps):
+            for _ in range(reps):
+                jp.debug_copy(bufs[i][0].array, bufs[i][1].array)
+
+        def run(reps):
+            th = [threading.Thread(target=worker, args=(i, reps)) for i in range(callers)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+
+        run(max(W, 1))
+        barrier()
+        t0 = time.perf_counter()
+        run(K)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        for hi, ho in bufs:
+            hi.free(); ho.free()
+        return ms
+
+    # Pageable caller blocks, as the unmodified reference allocates them (calloc, jampack.cpp:74-76): the library
+    # page-locks a block the first time it sees it, so the warm-up calls pay the registration and the timed ones do not.
+    def timed_host_pageable(direction, callers):
+        src = B if direction == "inverse" else T
+        bufs = [(np.array(src, copy=True), np.zeros(n + TRAILER, dtype=np.uint8)) for _ in range(callers)]
+        call = (lambda hi, ho: jp.inverse(hi, out=ho)) if direction == "inverse" else (lambda hi, ho: jp.forward(hi, out=ho))
+
+        def worker(i, reps):
+            for _ in range(reps):
+                call(*bufs[i])
+
+        def run(reps):
+            th = [threading.Thread(target=worker, args=(i, reps)) for i in range(callers)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+
+        t0 = time.perf_counter()
+        run(1)
+        first_ms = (time.perf_counter() - t0) * 1e3
+        run(max(W - 1, 1))
+        barrier()
+        t0 = time.perf_counter()
+        run(K)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        want = T if direction == "inverse" else B
+        ok = all(bool((ho[: want.size] == want).all()) for _, ho in bufs)
+        return ms, ok, first_ms
+
     # Device-resident throughput with `callers` blocks in flight on their own streams (same reason as above: a
     # block's latency-bound tails -- the end of each LF walk, the single-block scans -- overlap another block's work).
     def timed_device_concurrent(direction, callers):
@@ -400,6 +521,9 @@ def main():
     parity["round_trip"] = parity["round_trip"] and okc
     inv_c_ms, okc, inv_c_launches = timed_device_concurrent("inverse", CALLERS)
     parity["round_trip"] = parity["round_trip"] and okc
+    inv_copy_ms = timed_copy_ceiling("inverse", CALLERS)
+    inv_page_ms, okc, inv_page_first_ms = timed_host_pageable("inverse", CALLERS)
+    parity["round_trip"] = parity["round_trip"] and okc
 
     fwd = None
     if not args.no_forward:
@@ -411,7 +535,10 @@ def main():
         parity["forward_host_equals_device"] = parity["forward_host_equals_device"] and okc
         fwd_c_ms, okc, fwd_c_launches = timed_device_concurrent("forward", CALLERS)
         parity["forward_host_equals_device"] = parity["forward_host_equals_device"] and okc
-        fwd = (fwd_ms, fwd_acc, fwd_launches, fwd_stats, fwd_e2e_ms, fwd_e2e_c_ms, fwd_c_ms, fwd_c_launches)
+        fwd_copy_ms = timed_copy_ceiling("forward", CALLERS)
+        fwd_page_ms, okc, _ = timed_host_pageable("forward", CALLERS)
+        parity["forward_host_equals_device"] = parity["forward_host_equals_device"] and okc
+        fwd = (fwd_ms, fwd_acc, fwd_launches, fwd_stats, fwd_e2e_ms, fwd_e2e_c_ms, fwd_c_ms, fwd_c_launches, fwd_copy_ms, fwd_page_ms)
 
     clk = clocks.stop() if rank == 0 else None
 
@@ -419,11 +546,15 @@ def main():
     inv_e2e_max, _ = shard.reduce_step_stats(inv_e2e_ms, n * K, dev)
     inv_e2e_c_max, _ = shard.reduce_step_stats(inv_e2e_c_ms, n * K, dev)
     inv_c_max, _ = shard.reduce_step_stats(inv_c_ms, n * K, dev)
+    inv_copy_max, _ = shard.reduce_step_stats(inv_copy_ms, n * K, dev)
+    inv_page_max, _ = shard.reduce_step_stats(inv_page_ms, n * K, dev)
     if fwd:
         fwd_ms_max, _ = shard.reduce_step_stats(fwd[0], n * K, dev)
         fwd_e2e_max, _ = shard.reduce_step_stats(fwd[4], n * K, dev)
         fwd_e2e_c_max, _ = shard.reduce_step_stats(fwd[5], n * K, dev)
         fwd_c_max, _ = shard.reduce_step_stats(fwd[6], n * K, dev)
+        fwd_copy_max, _ = shard.reduce_step_stats(fwd[8], n * K, dev)
+        fwd_page_max, _ = shard.reduce_step_stats(fwd[9], n * K, dev)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -454,6 +585,13 @@ def main():
                         "mode": f"{CALLERS} concurrent host callers per GPU, one block each per step, through jp_bwt_inverse (how the "
                                 "reference's OpenMP block loop drives the stage); copies of one block overlap kernels of another",
                         "h2d_bytes_per_step": CALLERS * (n + TRAILER), "d2h_bytes_per_step": CALLERS * n, "host_memory": "pinned",
+                        "copy_ceiling": {"value": round(CALLERS * total_bytes / (inv_copy_max * 1e-3) / 1e6, 1), "unit": "MB/s",
+                                         "what": "the same callers, blocks and byte counts through jp_bwt_debug_copy: pinned H2D + D2H only, no kernels"},
+                        "frac_of_copy_ceiling": round(inv_copy_max / inv_e2e_c_max, 4),
+                        "pageable": {"value": round(CALLERS * total_bytes / (inv_page_max * 1e-3) / 1e6, 1), "unit": "MB/s",
+                                     "first_call_ms": round(inv_page_first_ms, 2),
+                                     "what": "the same callers with pageable (malloc) blocks, as the unmodified reference allocates them; the library "
+                                             "page-locks a block on first sight (first_call_ms includes that), later calls DMA directly"},
                         "single_caller": {"value": round(total_bytes / (inv_e2e_max * 1e-3) / 1e6, 1), "ms_per_step": round(inv_e2e_max / K, 4),
                                           "h2d_bytes_per_step": n + TRAILER, "d2h_bytes_per_step": n}},
                 "gpu_launches": inv_c_launches, "clocks": clk, "roofline": roof, "parity": parity,
@@ -471,9 +609,13 @@ def main():
                                "e2e": {"value": round(CALLERS * total_bytes / (fwd_e2e_c_max * 1e-3) / 1e6, 1), "unit": "MB/s",
                                        "blocks_per_step": CALLERS, "h2d_bytes_per_step": CALLERS * n, "d2h_bytes_per_step": CALLERS * (n + TRAILER),
                                        "host_memory": "pinned",
+                                       "copy_ceiling": {"value": round(CALLERS * total_bytes / (fwd_copy_max * 1e-3) / 1e6, 1), "unit": "MB/s"},
+                                       "frac_of_copy_ceiling": round(fwd_copy_max / fwd_e2e_c_max, 4),
+                                       "pageable": {"value": round(CALLERS * total_bytes / (fwd_page_max * 1e-3) / 1e6, 1), "unit": "MB/s"},
                                        "single_caller": {"value": round(total_bytes / (fwd_e2e_max * 1e-3) / 1e6, 1), "ms_per_step": round(fwd_e2e_max / K, 4)}},
                                "gpu_launches": fwd[7], "rounds": st["rounds"], "active_fraction": st["active_fraction"],
                                "symbol_bits": st["symbol_bits"], "initial_depth": st["initial_depth"], "device_bytes": st["device_bytes"],
+                               "workspace_bytes_per_byte": round(st["device_bytes"] / n, 2),
                                "roofline": {"bound": "hbm", "achieved": round(a_fwd / (f_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                             "frac": round(a_fwd / (f_ms * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": a_fwd,
                                             "random_bytes": r_fwd, "traffic": ncu_traffic("forward")},
@@ -494,6 +636,8 @@ def main():
                 if sb and sb["value"] > line["forward"]["cpu_baseline"]["value"]:
                     line["forward"]["cpu_baseline"].update(value=sb["value"], sample=sb["sample"])
             line["legacy_cuda_baseline"] = legacy_cuda_baseline(T, B)
+        if world == 1 and not args.no_configs:
+            line["configs"] = other_configs(jp, synth, torch, dev, not args.no_cpu_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

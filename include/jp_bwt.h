@@ -91,7 +91,13 @@ int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa);
 int jp_bwt_set_devices(const int* ids, int n);
 int jp_bwt_device_count(void);
 
-/* Pinned host blocks for callers that want direct DMA. */
+/* Starts creating the CUDA contexts of all configured devices in the background and returns at once: a host that
+ * knows it will call the stage (the shim's static initialiser does) hides the ~1 s per device behind its own start-up. */
+int jp_bwt_warmup_async(void);
+
+/* Pinned host blocks for callers that want direct DMA. Pageable blocks need no action: the host
+ * entry points page-lock a caller's block the first time they see it (the reference re-uses two blocks per Jampack
+ * instance for the whole run, jampack.cpp:74-76, :157-159); JP_BWT_HOST_REGISTER=0 disables that. */
 void* jp_bwt_host_alloc(uint64_t bytes);
 void  jp_bwt_host_free(void* p);
 
@@ -139,6 +145,9 @@ const char* jp_bwt_version(void);
  * jp_bwt_debug_gather_rate: random 4-byte gather micro-benchmark over a table of `table_bytes`
  *   (`chains` dependent walkers, `steps` each); returns sectors/s, or a negative error code. */
 int jp_bwt_debug_lf(const uint8_t* in, int32_t nlen, int32_t* lf, int32_t* ctable /*[257]*/);
+/* jp_bwt_debug_copy: only the host->device and device->host copies a stage call of these sizes makes (no kernels):
+ *   the ceiling bench.py reports its end-to-end figure against. */
+int jp_bwt_debug_copy(const uint8_t* in, int32_t in_len, uint8_t* out, int32_t out_len);
 double jp_bwt_debug_gather_rate(uint64_t table_bytes, int32_t chains, int32_t steps, int dependent);
 
 #ifdef __cplusplus

@@ -78,6 +78,8 @@ def lib():
         L.jp_bwt_suffix_array.argtypes = [C.c_void_p, C.c_int32, _i32p]
         L.jp_bwt_debug_gather_rate.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int]
         L.jp_bwt_debug_gather_rate.restype = C.c_double
+        L.jp_bwt_debug_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        L.jp_bwt_warmup_async.argtypes = []
         _lib = L
     return _lib
 
@@ -85,7 +87,7 @@ def lib():
 EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device", "jp_bwt_inverse_device_consume",
            "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free",
            "jp_bwt_last_stats", "jp_bwt_strerror", "jp_bwt_last_error_detail", "jp_bwt_version",
-           "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate"]
+           "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate", "jp_bwt_debug_copy", "jp_bwt_warmup_async"]
 
 
 def _check(rc, what):
@@ -260,6 +262,11 @@ def suffix_array(text):
 
 
 debug_suffix_array = suffix_array
+
+
+def debug_copy(src, dst):
+    """Only the copies of a stage call: host `src` -> device, device -> host `dst` (bench.py's copy ceiling)."""
+    _check(lib().jp_bwt_debug_copy(src.ctypes.data, src.size, dst.ctypes.data, dst.size), "jp_bwt_debug_copy")
 
 
 def debug_gather_rate(table_bytes, chains, steps, dependent=True):

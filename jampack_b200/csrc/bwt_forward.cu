@@ -119,6 +119,11 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 	const u32 radix = (u32)meta->sigma + 1;
 	__syncthreads();
 	const i64 base = (i64)blockIdx.x * KEY_TILE;
+	if (COMPACT) {                                     // a tile that lies inside a run has nothing to sort: leave before reading it
+		const i64 tile_end = min((i64)n, base + KEY_TILE);
+		const u32 next_base = (blockIdx.x + 1 < gridDim.x) ? skip_base[blockIdx.x + 1] : 0xffffffffu;
+		if (next_base == skip_base[blockIdx.x] && blockIdx.x + 1 < gridDim.x && tile_end > base) return;
+	}
 	for (int i = t; i < KEY_TILE + 64; i += 256) {
 		const i64 p = base + i;
 		sc[i] = p < n ? code[T[p]] : (u16)0;

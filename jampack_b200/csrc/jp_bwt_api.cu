@@ -2,6 +2,7 @@
 // sharding over devices, host<->device staging, error and stats plumbing. No kernels live here.
 #include "bwt_internal.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -116,9 +117,11 @@ static Trace g_trace[2];
 static std::atomic<int> g_trace_on{-1};
 static bool g_trace_calls = false;             // JP_BWT_TRACE=2: one line per call as well
 static long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static std::atomic<long long>& hostreg_counter(int which);
 static void trace_report()
 {
 	static const char* names[2] = {"forward", "inverse"};
+	fprintf(stderr, "[jp_bwt trace] host blocks page-locked on first sight: %lld (%.1f ms in cudaHostRegister)\n", hostreg_counter(0).load(), hostreg_counter(1).load() / 1e3);
 	for (int d = 0; d < 2; d++) {
 		const long long calls = g_trace[d].calls.load();
 		if (!calls) continue;
@@ -271,7 +274,7 @@ static int acquire(int device, Ctx** out)
 			const size_t nd = g_pool.devices.size();
 			for (size_t k = 0; k < nd; k++) {
 				const int d = g_pool.devices[(g_pool.rr + k) % nd];
-				if (g_pool.state[d] != 2) continue;
+				if (g_pool.state[d] != 2 && g_pool.state[d] != 4) continue;
 				int load = g_pool.pending[d];
 				for (auto& c : g_pool.ctxs) if (c->device == d && c->busy) load++;
 				if (load < best_load) { best_load = load; best = d; }
@@ -288,7 +291,7 @@ static int acquire(int device, Ctx** out)
 			device = best;
 			if (best_load < MAX_CTX_PER_DEVICE) g_pool.rr++;
 			else if (waited) warm_next_device_locked();          // every usable device has stayed full: widen the pool meanwhile
-		} else if (g_pool.state[device] != 2) {                  // an explicitly named device is brought up on the spot
+		} else if (g_pool.state[device] != 2 && g_pool.state[device] != 4) {   // an explicitly named device is brought up on the spot
 			g_pool.state[device] = 2;
 		}
 		int have = g_pool.pending[device];
@@ -372,6 +375,56 @@ static bool relieve_memory_pressure(Ctx& self)
 	return true;
 }
 
+// ---- caller blocks: page-lock them once ---------------------------------------------
+// The reference allocates its two ping-pong blocks once per Jampack instance (pageable calloc/realloc, jampack.cpp:74-76,
+// :157-159) and hands the same pointers to the stage for every block of the run. A pageable block goes through the
+// driver's bounce buffers (measured in the reference pipeline: 6-21 ms per 64 MiB copy); page-locking it the first
+// time it is seen (cudaHostRegister, ~10-20 ms once) turns every later copy into direct DMA. The cache is keyed by
+// the page-aligned range; a block that grows is registered again; at most HOSTREG_MAX ranges are kept (oldest out).
+// JP_BWT_HOST_REGISTER=0 turns it off. Blocks that are already page-locked (jp_bwt_host_alloc, a caller's own
+// cudaHostRegister) are recognised by cudaPointerGetAttributes and left alone.
+struct HostReg { uintptr_t lo, hi; unsigned long long stamp; };
+static std::mutex g_hostreg_mu;
+static std::vector<HostReg> g_hostreg;
+static unsigned long long g_hostreg_clock = 0;
+static std::atomic<long long> g_hostreg_count{0}, g_hostreg_us{0};
+constexpr size_t HOSTREG_MAX = 64, HOSTREG_MIN_BYTES = 1u << 20;
+static bool hostreg_enabled()
+{
+	static int v = -1;
+	if (v < 0) { const char* e = getenv("JP_BWT_HOST_REGISTER"); v = (e && *e == '0') ? 0 : 1; }
+	return v == 1;
+}
+static void hostreg_ensure(const void* p, size_t bytes)
+{
+	if (!hostreg_enabled() || !p || bytes < HOSTREG_MIN_BYTES) return;
+	const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
+	std::lock_guard<std::mutex> lk(g_hostreg_mu);
+	for (auto& r : g_hostreg) if (r.lo <= lo && hi <= r.hi) { r.stamp = ++g_hostreg_clock; return; }
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return; }
+	if (attr.type != cudaMemoryTypeUnregistered) return;                 // page-locked by its owner already
+	// ranges of ours that overlap the new one (the block grew, or was freed and its pages handed out again) go first
+	for (size_t i = 0; i < g_hostreg.size();) {
+		if (g_hostreg[i].lo < hi && lo < g_hostreg[i].hi) {
+			if (cudaHostUnregister((void*)g_hostreg[i].lo) != cudaSuccess) cudaGetLastError();
+			g_hostreg.erase(g_hostreg.begin() + (long)i);
+		} else i++;
+	}
+	if (g_hostreg.size() >= HOSTREG_MAX) {
+		size_t old = 0;
+		for (size_t i = 1; i < g_hostreg.size(); i++) if (g_hostreg[i].stamp < g_hostreg[old].stamp) old = i;
+		if (cudaHostUnregister((void*)g_hostreg[old].lo) != cudaSuccess) cudaGetLastError();
+		g_hostreg.erase(g_hostreg.begin() + (long)old);
+	}
+	const long long t0 = now_us();
+	if (cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return; }   // the copy still works, staged
+	g_hostreg_us += now_us() - t0; g_hostreg_count++;
+	g_hostreg.push_back(HostReg{lo, hi, ++g_hostreg_clock});
+}
+
+static std::atomic<long long>& hostreg_counter(int which) { return which == 0 ? g_hostreg_count : g_hostreg_us; }
+
 static void begin_call(Ctx& c)
 {
 	c.launches = 0;
@@ -422,6 +475,8 @@ static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 l
 	const size_t in_bytes = (size_t)in_len;
 	// forward: the trailer exists only when something was transformed (bwt.cpp:35)
 	const size_t out_bytes = direction == 0 ? (size_t)len + (nlen > 0 ? JP_BWT_TRAILER_BYTES : 0) : (size_t)len;
+	hostreg_ensure(in, in_bytes);
+	hostreg_ensure(out, (size_t)len + JP_BWT_TRAILER_BYTES);
 	JP_CUDA(cudaEventRecord(c.ev[8], s));
 	if (in_bytes) JP_CUDA(cudaMemcpyAsync(c.d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
 	JP_CUDA(cudaEventRecord(c.ev[9], s));
@@ -487,6 +542,60 @@ int jp_bwt_set_devices(const int* ids, int n)
 	if (g_pool.state.size() < (size_t)vis) g_pool.state.resize((size_t)vis, 0);
 	if (g_pool.state[d[0]] == 0) g_pool.state[d[0]] = 2;
 	g_pool.rr = 0;
+	return JP_OK;
+}
+
+int jp_bwt_warmup_async(void)
+{
+	// Starts bringing up the primary contexts of ALL configured devices in the background, one after the other (the
+	// driver serialises them anyway, about a second each): called by the shim's static initialiser, so that the
+	// start-up overlaps the reference's file read and LZ77 of the first batch instead of the first stage calls.
+	{
+		std::lock_guard<std::mutex> lk(g_pool.mu);
+		const int rc = init_devices_locked();
+		if (rc != JP_OK) return rc;
+		static bool started = false;
+		if (started) return JP_OK;
+		started = true;
+		for (int d : g_pool.devices) if (g_pool.state[d] == 0 || g_pool.state[d] == 2) g_pool.state[d] = g_pool.state[d] == 2 ? 4 : 1;   // 4: usable, context not forced yet
+		static bool hooked = false;
+		if (!hooked) {
+			hooked = true;
+			atexit([] {                                  // never tear the runtime down under a device that is coming up
+				for (int spin = 0; spin < 20000; spin++) {
+					{ std::lock_guard<std::mutex> lk2(g_pool.mu); bool busy = false; for (int st : g_pool.state) busy |= (st == 1); if (!busy) return; }
+					std::this_thread::sleep_for(std::chrono::milliseconds(1));
+				}
+			});
+		}
+	}
+	std::thread([] {
+		std::vector<int> devs;
+		{ std::lock_guard<std::mutex> lk(g_pool.mu); devs = g_pool.devices; }
+		for (int d : devs) {
+			{ std::lock_guard<std::mutex> lk(g_pool.mu); if (g_pool.state[d] != 1 && g_pool.state[d] != 4) continue; }
+			const bool ok = cudaSetDevice(d) == cudaSuccess && cudaFree(0) == cudaSuccess;
+			{ std::lock_guard<std::mutex> lk(g_pool.mu); g_pool.state[d] = ok ? 2 : 3; }
+			g_pool.cv.notify_all();
+		}
+	}).detach();
+	return JP_OK;
+}
+
+int jp_bwt_debug_copy(const uint8_t* in, int32_t in_len, uint8_t* out, int32_t out_len)
+{
+	// the host<->device copies of a stage call and nothing else: the ceiling of the end-to-end figure (bench.py)
+	if (!in || !out || in_len < 0 || out_len < 0) return JP_ERR_ARG;
+	CtxGuard g; JP_TRY(acquire(-1, &g.c));
+	Ctx& c = *g.c;
+	begin_call(c);
+	cudaStream_t s = c.own_stream;
+	JP_TRY(ensure_io(c, (size_t)std::max(in_len, out_len)));
+	hostreg_ensure(in, (size_t)in_len);
+	hostreg_ensure(out, (size_t)out_len);
+	if (in_len) JP_CUDA(cudaMemcpyAsync(c.d_in, in, (size_t)in_len, cudaMemcpyHostToDevice, s));
+	if (out_len) JP_CUDA(cudaMemcpyAsync(out, c.d_out, (size_t)out_len, cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaStreamSynchronize(s));
 	return JP_OK;
 }
 

@@ -15,6 +15,9 @@
 #endif
 #include "jp_bwt.h"
 
+// The CUDA contexts come up while the reference parses its arguments, reads the first batch and runs LZ77 on it.
+namespace { struct JpWarmup { JpWarmup() { jp_bwt_warmup_async(); } } jp_warmup_at_load; }
+
 void BlockSort::Bwt::ForwardBwt(Buffer Input, Buffer Output)
 {
 	int32_t out_len = 0;
