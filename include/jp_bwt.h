@@ -96,10 +96,15 @@ int jp_bwt_device_count(void);
 int jp_bwt_warmup_async(void);
 
 /* Pinned host blocks for callers that want direct DMA. Pageable blocks need no action: the host
- * entry points page-lock a caller's block the first time they see it (the reference re-uses two blocks per Jampack
- * instance for the whole run, jampack.cpp:74-76, :157-159); JP_BWT_HOST_REGISTER=0 disables that. */
+ * entry points page-lock a caller's block in the background once a first call on it has completed (the reference re-uses
+ * two blocks per Jampack instance for the whole run, jampack.cpp:74-76, :157-159), so every later call DMAs directly;
+ * JP_BWT_HOST_REGISTER=0 disables that. */
 void* jp_bwt_host_alloc(uint64_t bytes);
 void  jp_bwt_host_free(void* p);
+/* A caller that frees (or reallocates) a pageable block it has passed to jp_bwt_forward / jp_bwt_inverse while the
+ * library lives on tells it so BEFORE the free: the page-lock taken after its first call is dropped. p == NULL drops all.
+ * (The reference keeps its blocks for the whole run and needs no call.) */
+void  jp_bwt_host_release(const void* p);
 
 /* ---- diagnostics ----------------------------------------------------------------------------------*/
 typedef struct jp_bwt_stats {

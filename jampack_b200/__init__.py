@@ -48,6 +48,14 @@ class Stats(C.Structure):
 
 
 _lib = None
+# numpy blocks come and go: the array-level helpers give the page-lock back after every call unless the caller says the
+# blocks are long-lived (keep_host_blocks_locked(True): what a C++ host with persistent blocks gets by default)
+_release_after_call = True
+
+
+def keep_host_blocks_locked(keep):
+    global _release_after_call
+    _release_after_call = not keep
 
 
 def lib():
@@ -69,6 +77,8 @@ def lib():
         L.jp_bwt_host_alloc.restype = C.c_void_p
         L.jp_bwt_host_free.argtypes = [C.c_void_p]
         L.jp_bwt_host_free.restype = None
+        L.jp_bwt_host_release.argtypes = [C.c_void_p]
+        L.jp_bwt_host_release.restype = None
         L.jp_bwt_last_stats.argtypes = [C.POINTER(Stats)]
         L.jp_bwt_strerror.argtypes = [C.c_int]
         L.jp_bwt_strerror.restype = C.c_char_p
@@ -85,7 +95,7 @@ def lib():
 
 
 EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device", "jp_bwt_inverse_device_consume",
-           "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free",
+           "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free", "jp_bwt_host_release",
            "jp_bwt_last_stats", "jp_bwt_strerror", "jp_bwt_last_error_detail", "jp_bwt_version",
            "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate", "jp_bwt_debug_copy", "jp_bwt_warmup_async"]
 
@@ -134,6 +144,12 @@ class PinnedBlock:
             pass
 
 
+def host_release(array=None):
+    """Drops the page-lock the library took on a pageable block (all of them when `array` is None): call it before such
+    a block is freed while the library stays loaded."""
+    lib().jp_bwt_host_release(None if array is None else array.ctypes.data)
+
+
 # ---- array-level host entry points -------------------------------------------------------------------
 def forward(block, out=None, prefill=0):
     """BWT of a host block. Returns np.uint8[len + 480] (BWT bytes, raw tail, 120 int32 indices).
@@ -144,7 +160,11 @@ def forward(block, out=None, prefill=0):
         out = np.full(n + TRAILER, prefill, dtype=np.uint8)
     assert out.dtype == np.uint8 and out.size >= n + TRAILER and out.flags.c_contiguous
     ol = C.c_int32(0)
-    _check(lib().jp_bwt_forward(block.ctypes.data, n, out.ctypes.data, C.byref(ol)), "jp_bwt_forward")
+    try:
+        _check(lib().jp_bwt_forward(block.ctypes.data, n, out.ctypes.data, C.byref(ol)), "jp_bwt_forward")
+    finally:
+        if _release_after_call:
+            host_release(block); host_release(out)
     assert ol.value == n + TRAILER
     return out[: n + TRAILER]
 
@@ -156,7 +176,11 @@ def inverse(block, out=None):
     if out is None:
         out = np.zeros(max(n - TRAILER, 0), dtype=np.uint8)
     ol = C.c_int32(0)
-    _check(lib().jp_bwt_inverse(block.ctypes.data, n, out.ctypes.data, C.byref(ol)), "jp_bwt_inverse")
+    try:
+        _check(lib().jp_bwt_inverse(block.ctypes.data, n, out.ctypes.data, C.byref(ol)), "jp_bwt_inverse")
+    finally:
+        if _release_after_call:
+            host_release(block); host_release(out)
     assert ol.value == n - TRAILER
     return out[: n - TRAILER]
 

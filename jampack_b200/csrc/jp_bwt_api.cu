@@ -6,6 +6,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <stdarg.h>
@@ -121,7 +122,7 @@ static std::atomic<long long>& hostreg_counter(int which);
 static void trace_report()
 {
 	static const char* names[2] = {"forward", "inverse"};
-	fprintf(stderr, "[jp_bwt trace] host blocks page-locked on first sight: %lld (%.1f ms in cudaHostRegister)\n", hostreg_counter(0).load(), hostreg_counter(1).load() / 1e3);
+	fprintf(stderr, "[jp_bwt trace] host blocks page-locked in the background after their first call: %lld (%.1f ms in cudaHostRegister)\n", hostreg_counter(0).load(), hostreg_counter(1).load() / 1e3);
 	for (int d = 0; d < 2; d++) {
 		const long long calls = g_trace[d].calls.load();
 		if (!calls) continue;
@@ -378,14 +379,22 @@ static bool relieve_memory_pressure(Ctx& self)
 // ---- caller blocks: page-lock them once ---------------------------------------------
 // The reference allocates its two ping-pong blocks once per Jampack instance (pageable calloc/realloc, jampack.cpp:74-76,
 // :157-159) and hands the same pointers to the stage for every block of the run. A pageable block goes through the
-// driver's bounce buffers (measured in the reference pipeline: 6-21 ms per 64 MiB copy); page-locking it the first
-// time it is seen (cudaHostRegister, ~10-20 ms once) turns every later copy into direct DMA. The cache is keyed by
-// the page-aligned range; a block that grows is registered again; at most HOSTREG_MAX ranges are kept (oldest out).
-// JP_BWT_HOST_REGISTER=0 turns it off. Blocks that are already page-locked (jp_bwt_host_alloc, a caller's own
-// cudaHostRegister) are recognised by cudaPointerGetAttributes and left alone.
+// driver's bounce buffers (measured in the reference pipeline: 6-21 ms per 64 MiB copy). Page-locking it
+// (cudaHostRegister) turns every later copy into direct DMA, but costs 10-40 ms itself and stalls other CUDA calls while
+// it runs -- measured inside the calls of a one-batch run it made the run SLOWER. So the first call on a block copies
+// it as it is, and a background thread page-locks it afterwards, while the caller is busy with its other stages; from the
+// second call on the block is DMA'd directly. The cache is keyed by the page-aligned range; a block that grows is
+// registered again; at most HOSTREG_MAX ranges are kept (oldest out). JP_BWT_HOST_REGISTER=0 turns it off. Blocks that
+// are already page-locked (jp_bwt_host_alloc, a caller's own cudaHostRegister) are recognised and left alone.
 struct HostReg { uintptr_t lo, hi; unsigned long long stamp; };
-static std::mutex g_hostreg_mu;
-static std::vector<HostReg> g_hostreg;
+// (heap objects that are never destroyed: the worker thread is detached and sleeps on the condition variable, and
+// destroying a condition variable with a waiter -- which static destruction at exit would do -- blocks forever)
+static std::mutex& g_hostreg_mu = *new std::mutex;
+static std::condition_variable& g_hostreg_cv = *new std::condition_variable;
+static std::vector<HostReg>& g_hostreg = *new std::vector<HostReg>;            // registered ranges
+static std::vector<HostReg>& g_hostreg_todo = *new std::vector<HostReg>;       // ranges waiting for the worker
+static bool g_hostreg_worker = false, g_hostreg_busy = false;
+static uintptr_t g_hostreg_busy_lo = 0, g_hostreg_busy_hi = 0;
 static unsigned long long g_hostreg_clock = 0;
 static std::atomic<long long> g_hostreg_count{0}, g_hostreg_us{0};
 constexpr size_t HOSTREG_MAX = 64, HOSTREG_MIN_BYTES = 1u << 20;
@@ -395,35 +404,87 @@ static bool hostreg_enabled()
 	if (v < 0) { const char* e = getenv("JP_BWT_HOST_REGISTER"); v = (e && *e == '0') ? 0 : 1; }
 	return v == 1;
 }
-static void hostreg_ensure(const void* p, size_t bytes)
+static void hostreg_worker()
+{
+	std::unique_lock<std::mutex> lk(g_hostreg_mu);
+	for (;;) {
+		g_hostreg_cv.wait(lk, [] { return !g_hostreg_todo.empty(); });
+		const HostReg job = g_hostreg_todo.front();
+		g_hostreg_todo.erase(g_hostreg_todo.begin());
+		bool covered = false;
+		for (auto& r : g_hostreg) covered |= (r.lo <= job.lo && job.hi <= r.hi);
+		if (covered) continue;
+		// ranges of ours that overlap the new one (the block grew, or was freed and its pages handed out again) go first
+		for (size_t i = 0; i < g_hostreg.size();) {
+			if (g_hostreg[i].lo < job.hi && job.lo < g_hostreg[i].hi) {
+				if (cudaHostUnregister((void*)g_hostreg[i].lo) != cudaSuccess) cudaGetLastError();
+				g_hostreg.erase(g_hostreg.begin() + (long)i);
+			} else i++;
+		}
+		if (g_hostreg.size() >= HOSTREG_MAX) {
+			size_t old = 0;
+			for (size_t i = 1; i < g_hostreg.size(); i++) if (g_hostreg[i].stamp < g_hostreg[old].stamp) old = i;
+			if (cudaHostUnregister((void*)g_hostreg[old].lo) != cudaSuccess) cudaGetLastError();
+			g_hostreg.erase(g_hostreg.begin() + (long)old);
+		}
+		g_hostreg_busy = true; g_hostreg_busy_lo = job.lo; g_hostreg_busy_hi = job.hi;
+		lk.unlock();                                        // the page-locking itself runs outside the lock
+		{
+			// register through a device this process already uses (a fresh thread would otherwise open device 0)
+			int dev = -1;
+			{ std::lock_guard<std::mutex> pl(g_pool.mu); for (auto& cx : g_pool.ctxs) { dev = cx->device; break; } }
+			if (dev >= 0 && cudaSetDevice(dev) != cudaSuccess) cudaGetLastError();
+		}
+		const long long t0 = now_us();
+		cudaPointerAttributes attr;
+		bool ok = cudaPointerGetAttributes(&attr, (void*)job.lo) == cudaSuccess && attr.type == cudaMemoryTypeUnregistered;
+		if (ok) ok = cudaHostRegister((void*)job.lo, job.hi - job.lo, cudaHostRegisterPortable) == cudaSuccess;
+		if (!ok) cudaGetLastError();                        // (the copies still work, staged by the driver)
+		const long long t1 = now_us();
+		lk.lock();
+		g_hostreg_busy = false;
+		if (ok) { g_hostreg_us += t1 - t0; g_hostreg_count++; g_hostreg.push_back(HostReg{job.lo, job.hi, ++g_hostreg_clock}); }
+		g_hostreg_cv.notify_all();
+	}
+}
+// called when a stage call on [p, p + bytes) has completed
+static void hostreg_seen(const void* p, size_t bytes)
 {
 	if (!hostreg_enabled() || !p || bytes < HOSTREG_MIN_BYTES) return;
 	const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
 	std::lock_guard<std::mutex> lk(g_hostreg_mu);
 	for (auto& r : g_hostreg) if (r.lo <= lo && hi <= r.hi) { r.stamp = ++g_hostreg_clock; return; }
-	cudaPointerAttributes attr;
-	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return; }
-	if (attr.type != cudaMemoryTypeUnregistered) return;                 // page-locked by its owner already
-	// ranges of ours that overlap the new one (the block grew, or was freed and its pages handed out again) go first
+	for (auto& r : g_hostreg_todo) if (r.lo <= lo && hi <= r.hi) return;
+	if (g_hostreg_busy && g_hostreg_busy_lo <= lo && hi <= g_hostreg_busy_hi) return;
+	g_hostreg_todo.push_back(HostReg{lo, hi, 0});
+	if (!g_hostreg_worker) {
+		g_hostreg_worker = true;
+		std::thread(hostreg_worker).detach();
+		atexit([] {                                         // let a registration in progress finish before the runtime goes away
+			std::unique_lock<std::mutex> lk2(g_hostreg_mu);
+			g_hostreg_todo.clear();
+			g_hostreg_cv.wait_for(lk2, std::chrono::seconds(5), [] { return !g_hostreg_busy; });
+		});
+	}
+	g_hostreg_cv.notify_all();
+}
+static std::atomic<long long>& hostreg_counter(int which) { return which == 0 ? g_hostreg_count : g_hostreg_us; }
+// p == nullptr: every range; else the ranges that contain p
+static void hostreg_release(const void* p)
+{
+	std::unique_lock<std::mutex> lk(g_hostreg_mu);
+	const uintptr_t a = (uintptr_t)p;
+	for (size_t i = 0; i < g_hostreg_todo.size();) {
+		if (!p || (g_hostreg_todo[i].lo <= a && a < g_hostreg_todo[i].hi)) g_hostreg_todo.erase(g_hostreg_todo.begin() + (long)i); else i++;
+	}
+	g_hostreg_cv.wait(lk, [&] { return !g_hostreg_busy || (p && !(g_hostreg_busy_lo <= a && a < g_hostreg_busy_hi)); });
 	for (size_t i = 0; i < g_hostreg.size();) {
-		if (g_hostreg[i].lo < hi && lo < g_hostreg[i].hi) {
+		if (!p || (g_hostreg[i].lo <= a && a < g_hostreg[i].hi)) {
 			if (cudaHostUnregister((void*)g_hostreg[i].lo) != cudaSuccess) cudaGetLastError();
 			g_hostreg.erase(g_hostreg.begin() + (long)i);
 		} else i++;
 	}
-	if (g_hostreg.size() >= HOSTREG_MAX) {
-		size_t old = 0;
-		for (size_t i = 1; i < g_hostreg.size(); i++) if (g_hostreg[i].stamp < g_hostreg[old].stamp) old = i;
-		if (cudaHostUnregister((void*)g_hostreg[old].lo) != cudaSuccess) cudaGetLastError();
-		g_hostreg.erase(g_hostreg.begin() + (long)old);
-	}
-	const long long t0 = now_us();
-	if (cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return; }   // the copy still works, staged
-	g_hostreg_us += now_us() - t0; g_hostreg_count++;
-	g_hostreg.push_back(HostReg{lo, hi, ++g_hostreg_clock});
 }
-
-static std::atomic<long long>& hostreg_counter(int which) { return which == 0 ? g_hostreg_count : g_hostreg_us; }
 
 static void begin_call(Ctx& c)
 {
@@ -475,8 +536,6 @@ static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 l
 	const size_t in_bytes = (size_t)in_len;
 	// forward: the trailer exists only when something was transformed (bwt.cpp:35)
 	const size_t out_bytes = direction == 0 ? (size_t)len + (nlen > 0 ? JP_BWT_TRAILER_BYTES : 0) : (size_t)len;
-	hostreg_ensure(in, in_bytes);
-	hostreg_ensure(out, (size_t)len + JP_BWT_TRAILER_BYTES);
 	JP_CUDA(cudaEventRecord(c.ev[8], s));
 	if (in_bytes) JP_CUDA(cudaMemcpyAsync(c.d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
 	JP_CUDA(cudaEventRecord(c.ev[9], s));
@@ -491,6 +550,8 @@ static int host_call_once(Ctx& c, int direction, const u8* in, i32 in_len, i32 l
 	JP_CUDA(cudaEventElapsedTime(&t_stats.ms_d2h, c.ev[10], c.ev[11]));
 	t_stats.kernel_launches = c.launches;
 	t_stats.device_bytes = c.arena.high + c.arena2.high;
+	hostreg_seen(in, in_bytes);                             // page-locked in the background for the calls to come
+	hostreg_seen(out, (size_t)len + JP_BWT_TRAILER_BYTES);
 	return JP_OK;
 }
 
@@ -591,11 +652,11 @@ int jp_bwt_debug_copy(const uint8_t* in, int32_t in_len, uint8_t* out, int32_t o
 	begin_call(c);
 	cudaStream_t s = c.own_stream;
 	JP_TRY(ensure_io(c, (size_t)std::max(in_len, out_len)));
-	hostreg_ensure(in, (size_t)in_len);
-	hostreg_ensure(out, (size_t)out_len);
 	if (in_len) JP_CUDA(cudaMemcpyAsync(c.d_in, in, (size_t)in_len, cudaMemcpyHostToDevice, s));
 	if (out_len) JP_CUDA(cudaMemcpyAsync(out, c.d_out, (size_t)out_len, cudaMemcpyDeviceToHost, s));
 	JP_CUDA(cudaStreamSynchronize(s));
+	hostreg_seen(in, (size_t)in_len);
+	hostreg_seen(out, (size_t)out_len);
 	return JP_OK;
 }
 
@@ -609,9 +670,14 @@ int jp_bwt_device_count(void)
 void* jp_bwt_host_alloc(uint64_t bytes)
 {
 	void* p = nullptr;
-	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-	return p;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess) return p;
+	cudaGetLastError();
+	hostreg_release(nullptr);                       // page-locked memory is a limited resource: give the cached caller blocks back and retry
+	if (cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess) return p;
+	cudaGetLastError();
+	return nullptr;
 }
+void jp_bwt_host_release(const void* p) { hostreg_release(p); }
 void jp_bwt_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int jp_bwt_last_stats(jp_bwt_stats* out) { if (!out) return JP_ERR_ARG; *out = t_stats; return JP_OK; }
