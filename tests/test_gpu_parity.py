@@ -303,8 +303,18 @@ def test_text_with_long_repeats_takes_the_large_group_route(jp, orc):
     T = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
     T = T[: T.size - T.size % 120 + 7]
     want = orc.forward(T, _impl(orc))
-    got = jp.forward(T)
-    st = jp.last_stats()
+    got = jp.forward(T)                                     # as shipped: the runs of '=' are placed by the run bypass
+    assert (got == want).all() and jp.last_stats().bypass_runs > 0
+    saved = os.environ.get("JP_BWT_FWD_BYPASS")
+    os.environ["JP_BWT_FWD_BYPASS"] = "0"                   # without it they are over-long groups: the large-group route
+    try:
+        got = jp.forward(T)
+        st = jp.last_stats()
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_BYPASS", None)
+        else:
+            os.environ["JP_BWT_FWD_BYPASS"] = saved
     assert (got == want).all()
     assert st.large_fraction > 0, "expected some suffixes on the large-group route"
     assert (jp.inverse(got) == T).all()
