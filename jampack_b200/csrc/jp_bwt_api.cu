@@ -176,6 +176,7 @@ struct Pool {
 	unsigned rr = 0;
 };
 static Pool g_pool;
+static bool g_shutting_down = false;      // (under g_pool.mu)
 
 static int visible_devices()
 {
@@ -608,9 +609,14 @@ int jp_bwt_set_devices(const int* ids, int n)
 
 int jp_bwt_warmup_async(void)
 {
-	// Starts bringing up the primary contexts of ALL configured devices in the background, one after the other (the
-	// driver serialises them anyway, about a second each): called by the shim's static initialiser, so that the
-	// start-up overlaps the reference's file read and LZ77 of the first batch instead of the first stage calls.
+	// Starts bringing up primary contexts in the background: called by the shim's static initialiser, so that the
+	// start-up (0.3-2 s per device, and the driver creates them one after the other) overlaps the reference's file read
+	// and LZ77 of the first batch instead of the first stage calls. By default only the FIRST configured device is
+	// started here and the others follow on demand, when the usable ones stay saturated (warm_next_device_locked):
+	// measured through the reference CLI, a 1 GiB job keeps one B200 busy for a fraction of a second per batch, and
+	// every further context costs about a second to create and as much to tear down at exit -- with all of 4 devices
+	// started up front the decompression of that job took 7.9 s against 4.8 s on one (profiles/pipeline_*_r02.json).
+	// JP_BWT_WARM=all starts every configured device at load (long jobs on many GPUs).
 	{
 		std::lock_guard<std::mutex> lk(g_pool.mu);
 		const int rc = init_devices_locked();
@@ -618,11 +624,21 @@ int jp_bwt_warmup_async(void)
 		static bool started = false;
 		if (started) return JP_OK;
 		started = true;
-		for (int d : g_pool.devices) if (g_pool.state[d] == 0 || g_pool.state[d] == 2) g_pool.state[d] = g_pool.state[d] == 2 ? 4 : 1;   // 4: usable, context not forced yet
+		const char* mode = getenv("JP_BWT_WARM");
+		const bool all = mode && strcmp(mode, "all") == 0;
+		bool first = true;
+		for (int d : g_pool.devices) {
+			if (!all && !first) break;
+			if (g_pool.state[d] == 0 || g_pool.state[d] == 2) g_pool.state[d] = g_pool.state[d] == 2 ? 4 : 1;   // 4: usable, context not forced yet
+			first = false;
+		}
 		static bool hooked = false;
 		if (!hooked) {
 			hooked = true;
 			atexit([] {                                  // never tear the runtime down under a device that is coming up
+				const long long t0 = now_us();
+				{ std::lock_guard<std::mutex> lk2(g_pool.mu); g_shutting_down = true; }
+				struct Done { long long t0; ~Done() { if (g_trace_on.load() == 1) fprintf(stderr, "[jp_bwt warmup] exit waited %.3f s for start-ups in progress\n", (now_us() - t0) / 1e6); } } done{t0};
 				for (int spin = 0; spin < 20000; spin++) {
 					{ std::lock_guard<std::mutex> lk2(g_pool.mu); bool busy = false; for (int st : g_pool.state) busy |= (st == 1); if (!busy) return; }
 					std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -633,11 +649,18 @@ int jp_bwt_warmup_async(void)
 	std::thread([] {
 		std::vector<int> devs;
 		{ std::lock_guard<std::mutex> lk(g_pool.mu); devs = g_pool.devices; }
+		const long long t_load = now_us();
 		for (int d : devs) {
-			{ std::lock_guard<std::mutex> lk(g_pool.mu); if (g_pool.state[d] != 1 && g_pool.state[d] != 4) continue; }
+			{
+				std::lock_guard<std::mutex> lk(g_pool.mu);
+				if (g_pool.state[d] != 1 && g_pool.state[d] != 4) continue;
+				if (g_shutting_down) { if (g_pool.state[d] == 1) g_pool.state[d] = 0; continue; }   // the process is leaving: no more start-ups
+			}
+			const long long t0 = now_us();
 			const bool ok = cudaSetDevice(d) == cudaSuccess && cudaFree(0) == cudaSuccess;
 			{ std::lock_guard<std::mutex> lk(g_pool.mu); g_pool.state[d] = ok ? 2 : 3; }
 			g_pool.cv.notify_all();
+			if (trace_enabled()) fprintf(stderr, "[jp_bwt warmup] device %d %s after %.3f s (+%.3f s since load)\n", d, ok ? "up" : "FAILED", (now_us() - t0) / 1e6, (now_us() - t_load) / 1e6);
 		}
 	}).detach();
 	return JP_OK;
