@@ -85,6 +85,19 @@ int jp_bwt_inverse_device_consume(uint8_t* d_in, int32_t len_with_trailer, uint8
  * reference's own symbol name. n == 0 is a no-op. Returns JP_OK or an error code. */
 int jp_bwt_suffix_array(const uint8_t* in, int32_t n, int32_t* sa);
 
+/* ---- second stage, first half ------------------------------------------------------
+ * Sorted rank coding + RLE0 of a stage block, in the 1 MiB chunks of Ans::Encode (ans.cpp:134-160, ans.hpp:33): what
+ * Postcoder::Encode (rank.cpp:45-90) and RLE::encode (rle.cpp:22-47) compute per chunk, for every chunk at once. The
+ * adaptive rANS that follows (ans.cpp:162-221) is not part of it: a host (or a later kernel) consumes
+ *   freq[256 * k ..]            the 256 byte frequencies of chunk k (what WriteHeader stores, ans.cpp:282-286)
+ *   rle[JP_ANS_CHUNK * k ..]    the 16-bit RLE0 symbols of chunk k
+ *   rlen[k]                     their number
+ * for k < ceil(len / JP_ANS_CHUNK). The device form takes the block where jp_bwt_forward_device left it (d_in = that
+ * call's d_out, len = its len + 480): the BWT never leaves HBM between the two stages. */
+#define JP_ANS_CHUNK (1 << 20)
+int jp_src_rle0_device(const uint8_t* d_in, int32_t len, int32_t* d_freq, uint16_t* d_rle, int32_t* d_rlen, int device, void* stream);
+int jp_src_rle0(const uint8_t* in, int32_t len, int32_t* freq, uint16_t* rle, int32_t* rlen);
+
 /* ---- device selection (block sharding) ---------------------------------------------
  * Default: every visible device, or the list in the environment variable JP_BWT_DEVICES ("0,1,2").
  * jp_bwt_set_devices replaces the list (n = 0 restores the default). Returns JP_OK or an error. */
@@ -108,7 +121,7 @@ void  jp_bwt_host_release(const void* p);
 
 /* ---- diagnostics ----------------------------------------------------------------------------------*/
 typedef struct jp_bwt_stats {
-	int32_t  direction;          /* 0 forward, 1 inverse                                               */
+	int32_t  direction;          /* 0 forward, 1 inverse, 2 sorted rank coding + RLE0                  */
 	int32_t  len, nlen;
 	int32_t  device;
 	int32_t  kernel_launches;    /* kernels this call launched                                         */

@@ -88,6 +88,8 @@ def lib():
         L.jp_bwt_suffix_array.argtypes = [C.c_void_p, C.c_int32, _i32p]
         L.jp_bwt_debug_gather_rate.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int]
         L.jp_bwt_debug_gather_rate.restype = C.c_double
+        L.jp_src_rle0_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.jp_src_rle0.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.jp_bwt_debug_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.jp_bwt_warmup_async.argtypes = []
         _lib = L
@@ -97,7 +99,7 @@ def lib():
 EXPORTS = ["jp_bwt_forward", "jp_bwt_inverse", "jp_bwt_forward_device", "jp_bwt_inverse_device", "jp_bwt_inverse_device_consume",
            "jp_bwt_set_devices", "jp_bwt_device_count", "jp_bwt_host_alloc", "jp_bwt_host_free", "jp_bwt_host_release",
            "jp_bwt_last_stats", "jp_bwt_strerror", "jp_bwt_last_error_detail", "jp_bwt_version",
-           "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate", "jp_bwt_debug_copy", "jp_bwt_warmup_async"]
+           "jp_bwt_debug_lf", "jp_bwt_suffix_array", "jp_bwt_debug_gather_rate", "jp_bwt_debug_copy", "jp_bwt_warmup_async", "jp_src_rle0_device", "jp_src_rle0"]
 
 
 def _check(rc, what):
@@ -221,6 +223,37 @@ def inverse_device(d_in, d_out=None, consume=False):
     fn = lib().jp_bwt_inverse_device_consume if consume else lib().jp_bwt_inverse_device
     _check(fn(d_in.data_ptr(), n, d_out.data_ptr(), d_in.device.index or 0, _stream_of(d_in)), "jp_bwt_inverse_device")
     return d_out
+
+
+# ---- second stage, first half: sorted rank coding + RLE0 per 1 MiB chunk (reference rank.cpp:45-90, rle.cpp:22-47) ----
+ANS_CHUNK = 1 << 20        # ans.hpp:33 StackSize
+
+
+def src_rle0(block):
+    """Host block -> (freq int32[chunks, 256], rle: list of uint16 arrays, one per chunk)."""
+    block = np.ascontiguousarray(block, dtype=np.uint8)
+    n = block.size
+    nchunk = (n + ANS_CHUNK - 1) // ANS_CHUNK
+    freq = np.zeros((max(nchunk, 1), 256), dtype=np.int32)
+    rle = np.zeros(max(n, 1), dtype=np.uint16)
+    rlen = np.zeros(max(nchunk, 1), dtype=np.int32)
+    _check(lib().jp_src_rle0(block.ctypes.data, n, freq.ctypes.data, rle.ctypes.data, rlen.ctypes.data), "jp_src_rle0")
+    return freq[:nchunk], [rle[k * ANS_CHUNK: k * ANS_CHUNK + int(rlen[k])].copy() for k in range(nchunk)]
+
+
+def src_rle0_device(d_in):
+    """The same on a block that is resident in HBM (e.g. what forward_device returned): -> (freq, rle, rlen) CUDA tensors;
+    chunk k's symbols are rle[k * ANS_CHUNK : k * ANS_CHUNK + rlen[k]]."""
+    import torch
+    assert d_in.is_cuda and d_in.dtype == torch.uint8 and d_in.is_contiguous()
+    n = d_in.numel()
+    nchunk = (n + ANS_CHUNK - 1) // ANS_CHUNK
+    freq = torch.zeros((max(nchunk, 1), 256), dtype=torch.int32, device=d_in.device)
+    rle = torch.zeros(max(n, 1), dtype=torch.int16, device=d_in.device)
+    rlen = torch.zeros(max(nchunk, 1), dtype=torch.int32, device=d_in.device)
+    _check(lib().jp_src_rle0_device(d_in.data_ptr(), n, freq.data_ptr(), rle.data_ptr(), rlen.data_ptr(), d_in.device.index or 0, _stream_of(d_in)),
+           "jp_src_rle0_device")
+    return freq[:nchunk], rle, rlen[:nchunk]
 
 
 # ---- the reference's stage interface, mirrored ---------------------------------------------------------

@@ -58,6 +58,7 @@ template <typename T> inline T* arena_take(Ctx& c, size_t count)
 // scratch_in: nullptr, or d_in itself when the caller allows the input block to be overwritten (keeps the call at 6N)
 int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cudaStream_t s, jp_bwt_stats* st, u8* scratch_in);
 int forward_device(Ctx& c, const u8* d_in, i32 len, u8* d_out, cudaStream_t s, jp_bwt_stats* st);
+int src_rle0_device(Ctx& c, const u8* d_in, i32 len, i32* d_freq, u16* d_rle, i32* d_rlen, cudaStream_t s, jp_bwt_stats* st);
 
 // test hooks
 int debug_lf(Ctx& c, const u8* h_in, i32 nlen, i32* h_lf, i32* h_ctable);

@@ -590,6 +590,56 @@ int jp_bwt_forward_device(const uint8_t* d_in, int32_t len, uint8_t* d_out, int 
 int jp_bwt_inverse_device(const uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream) { return device_call(1, d_in, len_with_trailer, d_out, device, stream); }
 int jp_bwt_inverse_device_consume(uint8_t* d_in, int32_t len_with_trailer, uint8_t* d_out, int device, void* stream) { return device_call(1, d_in, len_with_trailer, d_out, device, stream, true); }
 
+int jp_src_rle0_device(const uint8_t* d_in, int32_t len, int32_t* d_freq, uint16_t* d_rle, int32_t* d_rlen, int device, void* stream)
+{
+	if (!d_in || !d_freq || !d_rle || !d_rlen || len < 0 || device < 0) { set_error_detail("null pointer, negative length or device"); return JP_ERR_ARG; }
+	if ((uintptr_t)d_in & 15) { set_error_detail("device blocks must be 16-byte aligned"); return JP_ERR_ARG; }
+	CtxGuard g;
+	JP_TRY(acquire(device, &g.c));
+	Ctx& c = *g.c;
+	cudaStream_t s = stream ? (cudaStream_t)stream : c.own_stream;
+	int rc = JP_ERR_OOM;
+	for (int attempt = 0; attempt < 256 && rc == JP_ERR_OOM; attempt++) {
+		if (attempt > 0 && !relieve_memory_pressure(c)) break;
+		begin_call(c);
+		rc = src_rle0_device(c, d_in, len, d_freq, d_rle, d_rlen, s, &t_stats);
+	}
+	t_stats.kernel_launches = c.launches;
+	return rc;
+}
+
+int jp_src_rle0(const uint8_t* in, int32_t len, int32_t* freq, uint16_t* rle, int32_t* rlen)
+{
+	if (!in || !freq || !rle || !rlen || len < 0) { set_error_detail("null pointer or negative length"); return JP_ERR_ARG; }
+	if (len == 0) return JP_OK;
+	CtxGuard g;
+	JP_TRY(acquire(-1, &g.c));
+	Ctx& c = *g.c;
+	cudaStream_t s = c.own_stream;
+	const size_t n = (size_t)len, nchunk = (n + JP_ANS_CHUNK - 1) / JP_ANS_CHUNK;
+	JP_TRY(ensure_io(c, n));                                            // d_in: the block
+	// outputs: one allocation per call (this entry point is a convenience for hosts without device buffers)
+	u8* d_o = nullptr;
+	const size_t b_rle = Arena::align(n * 2), b_freq = Arena::align(nchunk * 256 * 4), b_rlen = Arena::align(nchunk * 4);
+	JP_TRY(dev_alloc(c.device, (void**)&d_o, b_rle + b_freq + b_rlen));
+	struct Free { int dev; void* p; size_t b; ~Free() { dev_free(dev, p, b); } } fr{c.device, d_o, b_rle + b_freq + b_rlen};
+	u16* d_rle = (u16*)d_o; i32* d_freq = (i32*)(d_o + b_rle); i32* d_rlen = (i32*)(d_o + b_rle + b_freq);
+	JP_CUDA(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, s));
+	int rc = JP_ERR_OOM;
+	for (int attempt = 0; attempt < 256 && rc == JP_ERR_OOM; attempt++) {
+		if (attempt > 0 && !relieve_memory_pressure(c)) break;
+		begin_call(c);
+		rc = src_rle0_device(c, c.d_in, len, d_freq, d_rle, d_rlen, s, &t_stats);
+	}
+	if (rc != JP_OK) return rc;
+	JP_CUDA(cudaMemcpyAsync(freq, d_freq, nchunk * 256 * 4, cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaMemcpyAsync(rlen, d_rlen, nchunk * 4, cudaMemcpyDeviceToHost, s));
+	JP_CUDA(cudaMemcpyAsync(rle, d_rle, n * 2, cudaMemcpyDeviceToHost, s));   // (chunk k's symbols start at rle[k * JP_ANS_CHUNK])
+	JP_CUDA(cudaStreamSynchronize(s));
+	t_stats.kernel_launches = c.launches;
+	return JP_OK;
+}
+
 int jp_bwt_set_devices(const int* ids, int n)
 {
 	std::lock_guard<std::mutex> lk(g_pool.mu);

@@ -13,8 +13,12 @@ namespace jp {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_ITEMS   = 16;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per block
+#ifndef RS_ITEMS_CFG
+#define RS_ITEMS_CFG 16
+#endif
+constexpr int RS_ITEMS   = RS_ITEMS_CFG;            // pairs per thread (measured: profiles/radix_items_r02.md)
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // pairs per block
+static_assert(RS_TILE % 32 == 0 && RS_TILE % 16 == 0, "tiles are whole words of the run bitmap and whole 16-byte digit loads");
 constexpr size_t RS_SMEM_SCATTER = (size_t)RS_TILE * (8 + 4);
 
 __device__ __forceinline__ u32 rs_digit(u64 k, int shift) { return (u32)(k >> shift) & 255u; }
@@ -66,8 +70,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist_bytes(const u8* __restri
 	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
 	__syncthreads();
 	u32* hw = h[w];
-	const u32 p = blockIdx.x * RS_TILE + t * 16;        // RS_TILE = RS_THREADS * 16: one 16-byte load per thread
-	if (p + 16 <= n) {
+	const u32 p = blockIdx.x * RS_TILE + t * 16;        // one 16-byte load per thread (the first RS_TILE / 16 threads)
+	if (t * 16 >= RS_TILE) {}
+	else if (p + 16 <= n) {
 		const uint4 q = *reinterpret_cast<const uint4*>(digits + p);
 		const u32 wd[4] = {q.x, q.y, q.z, q.w};
 		u32 cur = wd[0] & 255u, run = 0;                // runs of equal digits (sorted data) fold into one atomic

@@ -55,6 +55,8 @@ def port():
         L.jpo_suffix_array_export.restype = C.c_int
         L.jpo_check_suffix_array.argtypes = [_u8p, _i32p, C.c_int32]
         L.jpo_check_suffix_array.restype = C.c_int
+        L.jpo_src_rle0.argtypes = [_u8p, C.c_int32, _i32p, C.POINTER(C.c_uint16), _i32p]
+        L.jpo_src_rle0.restype = C.c_int
         _port = L
     return _port
 
@@ -78,6 +80,9 @@ def ref():
         L.ref_core_count.restype = C.c_int
         L.ref_divsufsort.argtypes = [_u8p, _i32p, C.c_int]
         L.ref_divsufsort.restype = C.c_int
+        if hasattr(L, "ref_src_rle0"):
+            L.ref_src_rle0.argtypes = [_u8p, C.c_int, _i32p, C.POINTER(C.c_uint16), _i32p]
+            L.ref_src_rle0.restype = C.c_int
         _ref = L
     return _ref
 
@@ -149,3 +154,18 @@ def suffix_array(T, impl="port"):
         rc = port().jpo_suffix_array_export(_ptr(T), _ptr(SA, _i32p), T.size)
     assert rc == 0
     return SA
+
+
+def src_rle0(block, impl="port"):
+    """Sorted rank coding + RLE0 per 1 MiB chunk (ans.cpp:149-160) -> (freq int32[chunks, 256], list of uint16 arrays).
+    impl="ref": the reference's own Postcoder::Encode / RLE::encode (rank.cpp, rle.cpp compiled into oracle/_ref)."""
+    block = np.ascontiguousarray(block, dtype=np.uint8)
+    n = block.size
+    nchunk = (n + (1 << 20) - 1) >> 20
+    freq = np.zeros((max(nchunk, 1), 256), dtype=np.int32)
+    rle = np.zeros(max(nchunk, 1) << 20, dtype=np.uint16)
+    rlen = np.zeros(max(nchunk, 1), dtype=np.int32)
+    fn = ref().ref_src_rle0 if impl == "ref" else port().jpo_src_rle0
+    got = fn(_ptr(block), n, _ptr(freq, _i32p), rle.ctypes.data_as(C.POINTER(C.c_uint16)), _ptr(rlen, _i32p))
+    assert got == nchunk
+    return freq[:nchunk], [rle[(k << 20): (k << 20) + int(rlen[k])].copy() for k in range(nchunk)]

@@ -160,3 +160,65 @@ int jpo_check_suffix_array(const uint8_t* T, const int32_t* SA, int32_t n)
 	}
 	return 0;
 }
+
+/* ---- second stage, first half: sorted rank coding + RLE0, per 1 MiB chunk -----------------------------------------
+ * Restates what Ans::Encode does to a block before the entropy coder (reference ans.cpp:134-160): for every chunk of
+ * StackSize = 1 MiB (ans.hpp:33), Postcoder::Encode (rank.cpp:45-90) then RLE::encode (rle.cpp:22-47).
+ * freq[256 * k ..], rle[JPO_CHUNK * k ..] and rlen[k] receive chunk k's results. Returns the number of chunks. */
+#define JPO_CHUNK (1 << 20)
+int jpo_src_rle0(const uint8_t* T, int32_t len, int32_t* freq, uint16_t* rle, int32_t* rlen)
+{
+	int chunks = 0;
+	uint8_t* ranks = (uint8_t*)malloc(JPO_CHUNK);
+	if (!ranks) return -1;
+	for (int32_t in_p = 0; in_p < len; in_p += JPO_CHUNK, chunks++) {   /* ans.cpp:149-160 */
+		const uint8_t* C = T + in_p;
+		int32_t n = (in_p + JPO_CHUNK < len) ? JPO_CHUNK : (len - in_p);
+		int32_t* F = freq + 256 * chunks;
+		uint8_t S2R[256], R2S[256];
+		int32_t bucket[256];
+		int unique = 0;
+		memset(F, 0, 256 * sizeof(int32_t));
+		for (int32_t i = 0; i < n; i++) {                             /* rank.cpp:55-64: counts, list in order of first appearance */
+			uint8_t s = C[i];
+			if (F[s] == 0) { R2S[unique] = s; S2R[s] = (uint8_t)unique; unique++; }
+			F[s]++;
+		}
+		{                                                             /* rank.cpp:15-38, :66-72: buckets by descending count */
+			int32_t copy[256], pos = 0;
+			memcpy(copy, F, sizeof(copy));
+			for (int j = 0; j < 256; j++) {
+				int32_t max = 0; int best = 0;
+				for (int i = 0; i < 256; i++) if (copy[i] > max) { best = i; max = copy[i]; }
+				if (max == 0) break;
+				bucket[best] = pos; pos += F[best]; copy[best] = 0;
+			}
+		}
+		for (int32_t i = 0; i < n; i++) {                             /* rank.cpp:74-87: move to front, rank stored in the symbol's bucket */
+			uint8_t s = C[i], r = S2R[s];
+			ranks[bucket[s]++] = r;
+			if (r > 0) {
+				do { R2S[r] = R2S[r - 1]; S2R[R2S[r]] = r; } while (0 < --r);
+				R2S[0] = s; S2R[s] = 0;
+			}
+		}
+		{                                                             /* rle.cpp:22-47 */
+			uint16_t* out = rle + (size_t)JPO_CHUNK * chunks;
+			int32_t o = 0;
+			for (int32_t i = 0; i < n;) {
+				if (ranks[i] == 0) {
+					int32_t run = 1;
+					while (i + run < n && ranks[i + run] == 0) run++;
+					i += run;
+					int32_t L = run + 1, msb = 0;
+					for (int32_t v = L; v; v >>= 1) msb++;
+					msb -= 1;
+					while (msb--) out[o++] = (uint16_t)((L >> msb) & 1);
+				} else out[o++] = (uint16_t)(ranks[i++] + 1);
+			}
+			rlen[chunks] = o;
+		}
+	}
+	free(ranks);
+	return chunks;
+}

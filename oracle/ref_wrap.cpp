@@ -67,3 +67,26 @@ int ref_divsufsort(const unsigned char* T, int* SA, int n) { return divsufsort(T
 int ref_core_count(void) { return (int)GetCoreCount(); }
 
 }
+
+/* Second stage, first half, by the reference's own classes: what Ans::Encode does to each StackSize chunk before the
+ * entropy coder (ans.cpp:149-160) -- Postcoder::Encode (rank.cpp:45-90) then RLE::encode (rle.cpp:22-47). */
+#include "rank.hpp"
+#include "rle.hpp"
+extern "C" int ref_src_rle0(const unsigned char* in, int len, int* freq, unsigned short* rle, int* rlen)
+{
+	const int StackSize = 1 << 20;                       /* ans.hpp:33 */
+	Postcoder rank; RLE rle0;
+	unsigned char* tmp = (unsigned char*)malloc(StackSize + 16);
+	int chunks = 0;
+	for (int in_p = 0; in_p < len; in_p += StackSize, chunks++) {
+		int n = ((in_p + StackSize) < len) ? StackSize : (len - in_p);
+		memcpy(tmp, in + in_p, n);
+		tmp[n] = 0xA5;                                   /* rle.cpp:34 reads in[i + run] before it checks the bound */
+		rank.Encode(tmp, freq + 256 * chunks, n);
+		int rl = n;
+		rle0.encode(tmp, rle + (size_t)StackSize * chunks, &rl);
+		rlen[chunks] = rl;
+	}
+	free(tmp);
+	return chunks;
+}

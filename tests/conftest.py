@@ -24,3 +24,15 @@ def orc():
     import oracle
     oracle.port()   # builds oracle/_build on first use (gcc only)
     return oracle
+
+
+@pytest.fixture(scope="session")
+def jp():
+    """The product: libjpbwt.so through its Python mirror (GPU tests only; there is no CPU path to fall back on)."""
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import jampack_b200
+    from jampack_b200 import build
+    build.build()
+    assert jampack_b200.device_count() >= 1
+    return jampack_b200

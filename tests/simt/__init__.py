@@ -28,9 +28,9 @@ def build(force=False):
     if not force and not _stale():
         return LIB
     from . import gen
-    gen.main(["common.cuh", "bwt_internal.cuh", "radix_sort.cuh", "inv_stream.cuh", "bwt_inverse.cu", "bwt_forward.cu"])
+    gen.main(["common.cuh", "bwt_internal.cuh", "radix_sort.cuh", "inv_stream.cuh", "bwt_inverse.cu", "bwt_forward.cu", "src_rle0.cu"])
     cmd = ["g++", "-std=c++17", "-O1", "-w", "-fPIC", "-shared", "-I", HERE, "-I", OUT, "-o", LIB,
-           os.path.join(OUT, "bwt_inverse.cpp"), os.path.join(OUT, "bwt_forward.cpp"),
+           os.path.join(OUT, "bwt_inverse.cpp"), os.path.join(OUT, "bwt_forward.cpp"), os.path.join(OUT, "src_rle0.cpp"),
            os.path.join(HERE, "harness.cpp"), os.path.join(HERE, "simt_runtime.cpp")]
     env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
     subprocess.run(cmd, check=True, env=env)
@@ -44,6 +44,7 @@ def lib():
         L.emu_inverse.argtypes = [_u8p, C.c_int32, _u8p, C.c_int, _i32p, _i32p]
         L.emu_forward.argtypes = [_u8p, C.c_int32, _u8p, _i32p, _i32p]
         L.emu_suffix_array.argtypes = [_u8p, C.c_int32, _i32p]
+        L.emu_src_rle0.argtypes = [_u8p, C.c_int32, _i32p, C.POINTER(C.c_uint16), _i32p]
         _lib = L
     return _lib
 
@@ -73,3 +74,15 @@ def suffix_array(T):
     sa = np.zeros(max(T.size, 1), dtype=np.int32)
     rc = lib().emu_suffix_array(T.ctypes.data_as(_u8p), T.size, sa.ctypes.data_as(_i32p))
     return rc, sa[: T.size]
+
+
+def src_rle0(block):
+    """-> (rc, freq int32[chunks, 256], list of uint16 arrays) of the emulated jp::src_rle0_device"""
+    block = np.ascontiguousarray(block, dtype=np.uint8)
+    n = block.size
+    nchunk = (n + (1 << 20) - 1) >> 20
+    freq = np.zeros((max(nchunk, 1), 256), dtype=np.int32)
+    rle = np.zeros(max(n, 1), dtype=np.uint16)
+    rlen = np.zeros(max(nchunk, 1), dtype=np.int32)
+    rc = lib().emu_src_rle0(block.ctypes.data_as(_u8p), n, freq.ctypes.data_as(_i32p), rle.ctypes.data_as(C.POINTER(C.c_uint16)), rlen.ctypes.data_as(_i32p))
+    return rc, freq[:nchunk], [rle[(k << 20): (k << 20) + int(rlen[k])].copy() for k in range(nchunk)]

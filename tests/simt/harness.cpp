@@ -79,6 +79,19 @@ int emu_suffix_array(const uint8_t* in, int32_t n, int32_t* sa)
 	return jp::debug_suffix_array(c, in, n, sa);
 }
 
+/* sorted rank coding + RLE0 per 1 MiB chunk: freq[chunks][256], rle (chunk k at k << 20), rlen[chunks] */
+int emu_src_rle0(const uint8_t* in, int32_t len, int32_t* freq, uint16_t* rle, int32_t* rlen)
+{
+	jp::Ctx& c = jp::ctx();
+	const size_t n = (size_t)len;
+	uint8_t* d_in = (uint8_t*)aligned_alloc(256, (n + 511) & ~(size_t)255);
+	memcpy(d_in, in, n);
+	jp_bwt_stats st; memset(&st, 0, sizeof(st));
+	const int rc = jp::src_rle0_device(c, d_in, len, freq, rle, rlen, nullptr, &st);
+	free(d_in);
+	return rc;
+}
+
 int emu_forward(const uint8_t* in, int32_t len, uint8_t* out, int32_t* rounds, int32_t* launches)
 {
 	jp::Ctx& c = jp::ctx();

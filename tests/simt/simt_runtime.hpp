@@ -137,6 +137,8 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = simt::collective(simt::OP_SHFL_XOR, x, m); T r; memcpy(&r, &x, sizeof(T)); return r; }
 template <typename T> static inline unsigned __match_any_sync(unsigned, T v) { uint64_t x = 0; memcpy(&x, &v, sizeof(T)); return (unsigned)simt::collective(simt::OP_MATCH, x, 0); }
 
+static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o); return v; }
+
 void __syncthreads();
 int __syncthreads_or(int pred);
 

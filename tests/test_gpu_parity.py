@@ -14,17 +14,6 @@ MiB = 1 << 20
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def jp():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    import jampack_b200
-    from jampack_b200 import build
-    build.build()
-    assert jampack_b200.device_count() >= 1
-    return jampack_b200
-
-
 def _impl(orc):
     return "ref" if orc.ref() is not None else "port"
 
