@@ -36,7 +36,7 @@ constexpr u32 AP_POS  = 0x3fffffffu;     // ... and its position in SA (blocks s
 struct FwdMeta {
 	u32 code[256];
 	i32 sigma, bits, depth, key_bits;   // bits: per symbol (reported); depth: symbols per key; key_bits: bit length of the largest key
-	u32 eq4;                            // aligned 4-byte words of one repeated byte: a cheap screen for single-symbol runs
+	u32 eq4;                            // aligned 16-byte vectors of one repeated byte: a cheap screen for long single-symbol runs
 	u32 hist[256];
 };
 
@@ -55,8 +55,7 @@ __global__ void __launch_bounds__(256) k_fwd_symhist(const u8* __restrict__ T, i
 		if (p + 16 <= n) {
 			const uint4 q = __ldg(reinterpret_cast<const uint4*>(T + p));
 			const u32 wd[4] = {q.x, q.y, q.z, q.w};
-			#pragma unroll
-			for (int k = 0; k < 4; k++) eq4 += (wd[k] == (wd[k] & 255u) * 0x01010101u);
+			eq4 += (q.x == (q.x & 255u) * 0x01010101u && q.y == q.x && q.z == q.x && q.w == q.x) ? 1u : 0u;   // sixteen equal bytes
 			#pragma unroll
 			for (int k = 0; k < 16; k++) atomicAdd(&h[w][(wd[k >> 2] >> ((k & 3) * 8)) & 255], 1u);
 		} else for (i64 q = p; q < n; q++) atomicAdd(&h[w][T[q]], 1u);
@@ -717,7 +716,10 @@ constexpr int SG_ITEMS   = 16;
 constexpr int SG_CAP     = SG_THREADS * SG_ITEMS;   // 4096 elements sorted per block
 constexpr int SG_WIN     = SG_CAP / 2;              // window of group heads per block
 constexpr size_t SG_SMEM = (size_t)SG_CAP * (8 + 4);
-constexpr u32 SG_PAIR_MAX = 1024;                    // longest group the all-pairs rank refinement takes on
+#ifndef SG_PAIR_MAX_CFG
+#define SG_PAIR_MAX_CFG 1024
+#endif
+constexpr u32 SG_PAIR_MAX = SG_PAIR_MAX_CFG;             // longest group the all-pairs rank refinement takes on
 
 struct SegTile { u32 start, len; };
 
@@ -1244,11 +1246,13 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	if (bits < 1 || bits > 9 || depth < 7 || depth > 63 || key_bits0 < 1 || key_bits0 > 63) { set_error_detail("symbol remap gave bits=%d depth=%d key bits=%d", bits, depth, key_bits0); return JP_ERR_INTERNAL; }
 	st->symbol_bits = bits; st->initial_depth = depth;
 
-	// Run bypass: worth its detection pass when a visible share of the block sits in single-symbol runs (the histogram
-	// kernel counted aligned words of one repeated byte); JP_BWT_FWD_BYPASS=0/1 overrides the screen.
+	// Run bypass: worth its detection pass when a visible share of the block sits in long single-symbol runs. The histogram
+	// kernel counted the aligned 16-byte vectors of one repeated byte (every run of 31 bytes or more contains one; the
+	// 8-space indentation of source text does not): 1/64 of the block in such vectors engages the detection.
+	// JP_BWT_FWD_BYPASS=0/1 overrides the screen.
 	RunTabs rt = {};
 	u32 R = 0, M = 0;
-	bool bypass = (u64)(u32)c.h_small[20] * 4 * 32 >= (u64)n;
+	bool bypass = (u64)(u32)c.h_small[20] * 16 * 64 >= (u64)n;
 	if (const char* e = getenv("JP_BWT_FWD_BYPASS")) bypass = atoi(e) != 0;
 	const u32 ktiles = (u32)(((size_t)n + KEY_TILE - 1) / KEY_TILE);
 	if (bypass) {

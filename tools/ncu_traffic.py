@@ -29,7 +29,16 @@ if __name__ == "__main__":
     rows = load(sys.argv[1])
     for r in rows:
         print(f"{r['kernel']:24s} {r['ms']:8.4f} ms  read {r['read']/1e6:10.1f} MB  write {r['write']/1e6:10.1f} MB")
-    if "--update" in sys.argv:
+    if "--sum-all" in sys.argv:                       # every launch of the dump (one whole call captured with cudaProfilerStart/Stop)
+        path = sys.argv[sys.argv.index("--update") + 1]
+        key = sys.argv[sys.argv.index("--key") + 1]
+        d = json.load(open(path))
+        d[key] = int(round(sum(r["read"] + r["write"] for r in rows), -5))
+        d[key + "_launches"] = len(rows)
+        d[key + "_ms_under_ncu"] = round(sum(r["ms"] for r in rows), 3)
+        json.dump(d, open(path, "w"), indent=1)
+        print("updated", path, key, d[key], "over", len(rows), "launches")
+    elif "--update" in sys.argv:
         path = sys.argv[sys.argv.index("--update") + 1]
         key = sys.argv[sys.argv.index("--key") + 1]
         names = sys.argv[sys.argv.index("--sum") + 1].split(",")

@@ -44,7 +44,8 @@ def main():
         back = jp.inverse(want); s = jp.last_stats().asdict()
     ok_i = bool((back == T).all())
     print(f"forward ok={ok_f}: {fs['ms_total']:.2f} ms = {T.size / fs['ms_total'] / 1e6:.2f} GB/s (reference, 1 core+sssort threads: {t_ref:.1f} s); "
-          f"rounds={fs['rounds']} depth={fs['initial_depth']} a={fs['active_fraction']} phases={fs['ms_phase'][:7]}")
+          f"rounds={fs['rounds']} depth={fs['initial_depth']} sum_a={sum(fs['active_fraction']):.3f} large={fs['large_fraction']:.3f} radix_tiles={fs['radix_tiles']} "
+          f"bypass={fs['bypass_suffixes']}/{fs['bypass_runs']} period={fs['period']} ws={fs['device_bytes'] / T.size:.2f}N phases={[round(x, 3) for x in fs['ms_phase'][:5]]}")
     print(f"inverse ok={ok_i}: {s['ms_total']:.2f} ms = {T.size / s['ms_total'] / 1e6:.2f} GB/s phases={s['ms_phase'][:5]}")
     return 0 if ok_f and ok_i else 1
 
