@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256) k_run_fill(const u8* __restrict__ T, u32 
 	}
 	if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
 	__syncthreads();
-	if (t == 0) { if (LIST) rt.tile_base[blockIdx.x] = s_cnt; if (s_cnt) atomicAdd(&rt.counters[1], s_cnt); }
+	if (t == 0) { if (rt.tile_base) rt.tile_base[blockIdx.x] = s_cnt; if (s_cnt) atomicAdd(&rt.counters[1], s_cnt); }
 }
 
 // single block: tile_base[t] <- number of NON-run suffixes in the tiles before t
@@ -466,16 +466,17 @@ constexpr int GS_TILE    = GS_THREADS * GS_SUB;
 struct GAgg { i32 mh; u32 ns; u32 ng; u32 pad; };
 
 // head flags of the initial order: a key change
-__global__ void __launch_bounds__(256) k_fwd_flags(const u64* __restrict__ K, u32 n, u8* __restrict__ F)
+template <typename KT>
+__global__ void __launch_bounds__(256) k_fwd_flags(const KT* __restrict__ K, u32 n, u8* __restrict__ F)
 {
 	const u32 j0 = (blockIdx.x * 256 + threadIdx.x) * 4;
 	if (j0 >= n) return;
-	u64 prev = j0 ? K[j0 - 1] : ~K[0];
+	KT prev = j0 ? K[j0 - 1] : (KT)~K[0];
 	u32 w = 0;
 	#pragma unroll
 	for (int b = 0; b < 4; b++) {
 		const u32 j = j0 + b;
-		if (j < n) { const u64 k = K[j]; w |= (k != prev ? 1u : 0u) << (8 * b); prev = k; }
+		if (j < n) { const KT k = K[j]; w |= (k != prev ? 1u : 0u) << (8 * b); prev = k; }
 	}
 	if (j0 + 4 <= n) *reinterpret_cast<u32*>(F + j0) = w;
 	else for (int b = 0; b < 4 && j0 + b < n; b++) F[j0 + b] = (u8)(w >> (8 * b));
@@ -637,11 +638,19 @@ __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, 
 
 // ---- 5. doubling rounds ----------------------------------------------------------------------------------
 // key2 of suffix v in the round with offset h. (The template parameter selects the periodic-run keys added below.)
-struct PerSkip { const u32* rl; const u32* bits; const u8* T; u32 p; u32 first; };
+struct PerSkip { const u32* rl; const u32* bits; const u8* T; u32 p; u32 first; u32 redirect; u32 deep; };
 
 template <bool PS>
 __device__ __forceinline__ u32 key2_of(u32 v, u32 h, u32 n, const u32* __restrict__ ISA, const PerSkip& ps, int* __restrict__ err)
 {
+	if (PS && ps.redirect) {
+		// reduced sort of a periodic block (see "periodic blocks are sorted through their representatives"): a skipped
+		// suffix answers with the rank of the representative of its stretch and phase
+		u32 x = v + h;
+		if (x > n) { dev_fail(err, DE_FWD_RANGE); x = n; }
+		if (x < n && ((__ldg(&ps.bits[x >> 5]) >> (x & 31)) & 1u)) x += ps.p * ((__ldg(&ps.rl[x]) - ps.deep) / ps.p);
+		return __ldg(&ISA[x]);
+	}
 	if (PS) {
 		if ((__ldg(&ps.bits[v >> 5]) >> (v & 31)) & 1u) {
 			const u32 r = __ldg(&ps.rl[v]);                    // v + r <= n by construction, r >= p
@@ -704,6 +713,64 @@ __global__ void __launch_bounds__(1024) k_per_pick(const u32* __restrict__ hist,
 		for (int k = 1; k < 32; k++) if (sc[k] > best || (sc[k] == best && sd[k] < bd)) { best = sc[k]; bd = sd[k]; }
 		out[0] = bd; out[1] = best;
 	}
+}
+
+// ---- 5q. periodic blocks are sorted through their representatives -----------------------------------------------
+// The rounds with h < p are the expensive part of a periodic block: nothing can be skipped in them (members of a group
+// share fewer than p symbols), yet nearly all of the block is copies of the same p rotations. When the period is known
+// BEFORE the sort they are run on a fraction of the block. With H = the first doubling distance >= p: a suffix is DEEP
+// when r(v) >= H (its first H symbols are periodic), and among the deep suffixes of one stretch and phase -- v, v + p,
+// v + 2p, ... -- the last one is their REPRESENTATIVE; the others (r(v) >= H + p) are skipped. Representatives and
+// non-deep suffixes -- a few percent of the block -- are sorted by the ordinary machinery: initial keys, then the
+// rounds h = depth .. H/2, in which a lookup that lands on a skipped suffix x is answered by its representative
+// x + p * floor((r(x) - H) / p), whose first H symbols are x's own. That leaves them exactly H-ordered. A skipped suffix
+// shares its first H symbols with its representative, so giving it the representative's rank as its key and sorting the
+// WHOLE block once by that 3-byte key yields the H-order of all suffixes (ties = H-equal), from which the ordinary flow
+// continues at h = H with the repeat-length keys of the previous section. `repetitive(64 MiB)`: the six rounds over
+// 67 M suffixes (6.2 ms each) become six rounds over 4 M, and the eight 12-byte radix passes of the initial sort three
+// 8-byte ones. The period is found in the text itself: for 64 sampled positions, the distance to the next occurrence
+// of the 32 bytes that follow; if half of the samples agree, that distance is p (0.02 ms on a block without a period).
+constexpr u32 PROBE_SAMPLES = 64, PROBE_WIN = 32;
+// one block per sample: thread t tries the distances t + 1, t + 257, ...; the block stops at the first round that has a hit
+__global__ void __launch_bounds__(256) k_per_probe(const u8* __restrict__ T, u32 n, u32* __restrict__ out)
+{
+	__shared__ u32 s_found;
+	const u32 t = threadIdx.x, sample = blockIdx.x;
+	const u32 span = PER_MAXP + PROBE_WIN;
+	if (t == 0) s_found = 0xffffffffu;
+	__syncthreads();
+	if (n > 2 * span) {
+		const u32 a = (u32)(((u64)sample * (u64)(n - span - 1)) / PROBE_SAMPLES);
+		const u32 w0 = (u32)T[a] | ((u32)T[a + 1] << 8) | ((u32)T[a + 2] << 16) | ((u32)T[a + 3] << 24);
+		for (u32 d0 = 1; d0 < PER_MAXP; d0 += 2048) {                  // eight distances per thread between two barriers
+			bool any = false;
+			#pragma unroll 2
+			for (u32 k8 = 0; k8 < 8; k8++) {
+				const u32 d = d0 + k8 * 256 + t;
+				if (d >= PER_MAXP) break;
+				const u8* q = T + a + d;
+				if (((u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24)) != w0) continue;
+				bool hit = true;
+				for (u32 k = 4; k < PROBE_WIN; k++) if (q[k] != T[a + k]) { hit = false; break; }
+				if (hit) { atomicMin(&s_found, d); any = true; break; }
+			}
+			if (__syncthreads_or(any ? 1 : 0)) break;
+		}
+	}
+	__syncthreads();
+	if (t == 0) out[sample] = s_found == 0xffffffffu ? 0u : s_found;
+}
+
+// key of every suffix for the one sort of the whole block: the rank of itself (reduced set) or of its representative
+__global__ void __launch_bounds__(256) k_per_expand(const u32* __restrict__ ISA, const u32* __restrict__ RL, const u32* __restrict__ skip, u32 p, u32 deep, u32 n,
+                                                    u32* __restrict__ K, u32* __restrict__ V)
+{
+	const u32 v = blockIdx.x * 256 + threadIdx.x;
+	if (v >= n) return;
+	u32 x = v;
+	if ((skip[v >> 5] >> (v & 31)) & 1u) x += p * ((RL[v] - deep) / p);
+	K[v] = ISA[x];
+	V[v] = v;
 }
 
 // ---- 5a. small groups: gather + segmented sort in shared memory -----------------------------------------
@@ -1229,6 +1296,35 @@ static int run_tabs_alloc(Ctx& c, i32 n, u32 tiles, RunTabs& rt)
 	return JP_OK;
 }
 
+// Repeat lengths r(v) of period p for every position (second arena): bit v of `bits` = r(v) >= thr; returns the number of
+// set bits in *count (after the caller's next synchronisation, through h_small[15]).
+struct PerTabs { u32* bits; u32* tile_first; u32* tile_next; u32* tile_base; u32* RL; u32* counters; u32* probe; size_t keep; };
+static int per_tabs_alloc(Ctx& c, i32 n, u32 tiles, PerTabs& t)
+{
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
+	const size_t o_bits = take(((size_t)n / 32 + 2) * 4), o_tf = take((size_t)tiles * 4), o_tn = take((size_t)tiles * 4), o_tb = take((size_t)tiles * 4),
+	             o_rl = take((size_t)n * 4), o_ct = take(64);
+	t.keep = off;                                                       // everything up to here survives a later growth of the arena
+	const size_t o_hist = take((size_t)PER_MAXP * 4 + 64);
+	JP_TRY(arena2_reserve(c, off));
+	u8* a2 = c.arena2.base;
+	t.bits = (u32*)(a2 + o_bits); t.tile_first = (u32*)(a2 + o_tf); t.tile_next = (u32*)(a2 + o_tn); t.tile_base = (u32*)(a2 + o_tb);
+	t.RL = (u32*)(a2 + o_rl); t.counters = (u32*)(a2 + o_ct); t.probe = (u32*)(a2 + o_hist);
+	return JP_OK;
+}
+static int per_tabs_fill(Ctx& c, const u8* d_T, i32 n, u32 tiles, u32 p, u32 thr, PerTabs& t, cudaStream_t s)
+{
+	RunTabs pt = {};
+	pt.bits = t.bits; pt.tile_first = t.tile_first; pt.tile_next = t.tile_next; pt.tile_base = t.tile_base; pt.counters = t.counters;
+	JP_CUDA(cudaMemsetAsync(t.counters, 0, 64, s));
+	k_run_first<<<tiles, 256, 0, s>>>(d_T, (u32)n, p, t.tile_first); JP_LAUNCH(c);
+	k_run_scan<<<1, 1024, 0, s>>>(t.tile_first, tiles, t.tile_next); JP_LAUNCH(c);
+	k_run_fill<false><<<tiles, 256, 0, s>>>(d_T, (u32)n, p, t.tile_next, thr, pt, t.RL); JP_LAUNCH(c);
+	JP_KCHECK();
+	return JP_OK;
+}
+
 // Builds SA and ISA (ranks 1..n; ISA[n] = 0) of T[0..n) in b. Events ev[1..4] mark the phase boundaries.
 static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t s, jp_bwt_stats* st)
 {
@@ -1239,12 +1335,198 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	const int hblocks = (int)(hwant < hcap ? hwant : hcap);
 	k_fwd_symhist<<<hblocks, 256, 0, s>>>(d_T, n, b.meta); JP_LAUNCH(c);
 	k_fwd_codes<<<1, 256, 0, s>>>(b.meta); JP_LAUNCH(c);
+	// period probe (sorting a periodic block through its representatives): the samples land in the radix histogram area
+	int want_probe = n >= (1 << 20) ? 1 : 0;
+	if (const char* e = getenv("JP_BWT_FWD_REDUCED")) want_probe = atoi(e) != 0 && (u32)n > 2 * (PER_MAXP + PROBE_WIN) ? 1 : 0;
+	if (want_probe) { k_per_probe<<<PROBE_SAMPLES, 256, 0, s>>>(d_T, (u32)n, b.rb.tile_hist); JP_LAUNCH(c); }
 	JP_KCHECK();
+	u32 h_probe[PROBE_SAMPLES];
+	if (want_probe) JP_CUDA(cudaMemcpyAsync(h_probe, b.rb.tile_hist, sizeof(h_probe), cudaMemcpyDeviceToHost, s));
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 5 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth, key_bits, eq4
 	JP_CUDA(cudaStreamSynchronize(s));
 	const int bits = c.h_small[17], depth = c.h_small[18], key_bits0 = c.h_small[19];
 	if (bits < 1 || bits > 9 || depth < 7 || depth > 63 || key_bits0 < 1 || key_bits0 > 63) { set_error_detail("symbol remap gave bits=%d depth=%d key bits=%d", bits, depth, key_bits0); return JP_ERR_INTERNAL; }
 	st->symbol_bits = bits; st->initial_depth = depth;
+	const u32 ktiles = (u32)(((size_t)n + KEY_TILE - 1) / KEY_TILE);
+	if (cudaFuncSetAttribute(k_seg_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_seg_sort_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
+
+	// ---- state of the doubling rounds (shared by the reduced sort of a periodic block and the main loop) ----
+	int rank_bits = bit_length((u64)n);                                 // key2 is a rank <= n (a repeat-length key <= 2n + 1)
+	int act = 0;
+	u32 A = 0, G = 0;
+	u64 sectors = 2ull * (u64)n;
+	i64 h = depth;
+	int rounds = 0;
+	PerSkip ps; ps.rl = nullptr; ps.bits = nullptr; ps.T = d_T; ps.p = 1; ps.first = 0; ps.redirect = 0; ps.deep = 0;
+	bool periodic = false, reduced = false;
+	int pass = 0;                                                       // 0: pass A still to come, 1: pass B next (same h), 2: both done
+	i64 h_a = 0;                                                        // the h of pass A: first h >= p
+	size_t keep2 = 0;                                                   // bytes at the start of the second arena that later growth must keep
+	const bool trace_rounds = getenv("JP_BWT_TRACE_ROUNDS") != nullptr;      // one stderr line per doubling round (host wall time)
+	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	std::vector<u32> h_off;
+	auto run_rounds = [&](i64 h_stop) -> int {
+		while (A > 0 && h < h_stop) {
+			if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
+			if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
+			st->active_fraction[rounds] = (float)((double)A / (double)n);
+			sectors += 2ull * A;
+			double large_frac_now = 0.0;
+			const u32* AP = b.AP[act];
+			const bool use_ps = reduced || (periodic && h >= h_a);           // repeat-length keys from the first h >= p on; redirected lookups in the reduced sort
+			ps.redirect = reduced ? 1u : 0u;
+			ps.first = (!reduced && use_ps && pass == 0) ? 1u : 0u;
+			// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
+			// shared-memory radix kernel; groups longer than a window are reported for the large-group route
+			const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
+			JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
+			if (use_ps) k_seg_sort<true><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
+			else k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
+			JP_LAUNCH(c);
+			JP_KCHECK();
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaStreamSynchronize(s));
+			const bool large = c.h_small[10] != 0;
+			const u32 queued = (u32)c.h_small[11];
+			if (queued) {
+				if (use_ps) k_seg_sort_radix<true><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
+				else k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
+				JP_LAUNCH(c);
+				JP_KCHECK();
+				st->radix_tiles += (i32)queued;
+			}
+			if (large) {
+				k_large_collect<<<1, 1024, 0, s>>>(b.win_first, b.win_large, nwin, A, b.lg_head, b.lg_off, b.counters); JP_LAUNCH(c);
+				JP_KCHECK();
+				JP_CUDA(cudaMemcpyAsync(c.h_small + 12, b.counters + 4, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+				JP_CUDA(cudaStreamSynchronize(s));
+				const u32 ng = (u32)c.h_small[12], total = (u32)c.h_small[13];
+				st->large_fraction += (float)((double)total / (double)n);   // share of the block on the large-group route, summed over rounds
+				large_frac_now = (double)total / (double)A;
+				if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
+				// Scratch of the sort: the spare unit, the staging unit and the idle active buffer hold (8 + 8 + 2 x 4) bytes for
+				// up to N/2 suffixes. More than that (blocks that are mostly long repeats) goes through in batches of whole groups;
+				// a single group beyond N/2 falls back on the second arena.
+				const u32 cap = (u32)(b.usz / 8);
+				if (total > cap) {
+					h_off.resize((size_t)ng + 1);
+					JP_CUDA(cudaMemcpyAsync(h_off.data(), b.lg_off, ((size_t)ng + 1) * 4, cudaMemcpyDeviceToHost, s));
+					JP_CUDA(cudaStreamSynchronize(s));
+				}
+				for (u32 g0 = 0; g0 < ng;) {
+					u32 g1 = ng, x0 = 0, count = total;
+					if (total > cap) {
+						g1 = g0 + 1;
+						while (g1 < ng && h_off[g1 + 1] - h_off[g0] <= cap) g1++;
+						x0 = h_off[g0]; count = h_off[g1] - x0;
+					}
+					RadixBuffers lb = b.rb;
+					lb.dnext = nullptr;                         // the flag bytes of this round are live in b.F
+					if (count <= cap) {
+						lb.k[0] = reinterpret_cast<u64*>(b.X); lb.k[1] = reinterpret_cast<u64*>(b.VS);
+						lb.v[0] = b.AP[act ^ 1]; lb.v[1] = b.AP[act ^ 1] + b.usz / 8;
+					} else {
+						const size_t T8 = Arena::align((size_t)count * 8), T4 = Arena::align((size_t)count * 4), base = Arena::align(keep2);
+						JP_TRY(arena2_reserve(c, base + 2 * T8 + 2 * T4, keep2));
+						u8* a2 = c.arena2.base;
+						if (periodic) { ps.bits = (const u32*)a2; ps.rl = (const u32*)(a2 + ((const u8*)ps.rl - (const u8*)ps.bits)); }
+						lb.k[0] = reinterpret_cast<u64*>(a2 + base); lb.k[1] = reinterpret_cast<u64*>(a2 + base + T8);
+						lb.v[0] = reinterpret_cast<u32*>(a2 + base + 2 * T8); lb.v[1] = reinterpret_cast<u32*>(a2 + base + 2 * T8 + T4);
+					}
+					if (use_ps) k_large_extract<true><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
+					else k_large_extract<false><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
+					JP_LAUNCH(c);
+					const int key_bits = rank_bits + bit_length((u64)(g1 - g0 - 1));
+					const int lc = radix_sort_pairs(lb, 0, count, 0, key_bits, s, &c.launches);
+					if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+					k_large_writeback<<<(count + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, g0, x0, count, AP, b.SA, b.F); JP_LAUNCH(c);
+					JP_KCHECK();
+					g0 = g1;
+				}
+			}
+			JP_TRY(group_step(c, b, AP, b.AP[act ^ 1], A, s));
+			if (trace_rounds) {
+				const double t1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+				fprintf(stderr, "[jp_bwt round] %d h=%lld%s active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h,
+				        reduced ? " (representatives)" : use_ps ? (pass == 0 ? " (repeat lengths)" : " (repeat jumps)") : "", A, G, (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
+				t_round = t1;
+			}
+			act ^= 1;
+			A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
+			if (!reduced && use_ps && pass == 0) pass = 1;                   // pass B repeats this h
+			else { h *= 2; if (!reduced && use_ps) pass = 2; }
+			rounds++;
+		}
+		return JP_OK;
+	};
+
+	// ---- a periodic block is sorted through its representatives ("5q") -------------------------------------------
+	bool premode = false;
+	PerTabs pt = {};
+	u32 per_p = 0;
+	if (want_probe) {
+		std::sort(h_probe, h_probe + PROBE_SAMPLES);
+		u32 best = 0, best_cnt = 0;
+		for (u32 i = 0; i < PROBE_SAMPLES;) { u32 j = i; while (j < PROBE_SAMPLES && h_probe[j] == h_probe[i]) j++; if (h_probe[i] != 0 && j - i > best_cnt) { best = h_probe[i]; best_cnt = j - i; } i = j; }
+		i64 H = depth;
+		while (H < (i64)best) H *= 2;
+		if (best >= 2 && best_cnt * 2 >= PROBE_SAMPLES && H * 8 <= (i64)n) {
+			per_p = best;
+			JP_TRY(per_tabs_alloc(c, n, ktiles, pt));
+			JP_TRY(per_tabs_fill(c, d_T, n, ktiles, per_p, (u32)(H + per_p), pt, s));      // bit = skipped: deep, and not the last deep one of its stretch and phase
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 14, pt.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+			JP_CUDA(cudaStreamSynchronize(s));
+			const u32 skipped = (u32)c.h_small[15];
+			premode = (u64)skipped * 2 >= (u64)n;                          // worth it when at least half of the block is skipped
+			if (premode) {
+				const u32 n_red = (u32)n - skipped;
+				h_a = H;
+				k_run_tile_scan<<<1, 1024, 0, s>>>(pt.tile_base, ktiles, (u32)n); JP_LAUNCH(c);
+				k_fwd_keys<true><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], nullptr, 0, pt.bits, pt.tile_base); JP_LAUNCH(c);
+				JP_KCHECK();
+				JP_CUDA(cudaEventRecord(c.ev[1], s));
+				const int cur = radix_sort_pairs(b.rb, 0, n_red, 0, key_bits0, s, &c.launches);
+				if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+				b.ISA = reinterpret_cast<u32*>(b.unit[cur ? 0 : 2]);
+				b.X = reinterpret_cast<u32*>(b.unit[cur ? 1 : 3]);
+				b.AP[0] = reinterpret_cast<u32*>(b.unit[cur ? 2 : 0]);
+				b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
+				b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
+				k_fwd_flags<u64><<<(n_red + 1023) / 1024, 256, 0, s>>>(b.rb.k[cur], n_red, b.F); JP_LAUNCH(c);
+				JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));
+				JP_TRY(group_step(c, b, nullptr, b.AP[0], n_red, s));         // ranks 1..n_red of the reduced set
+				A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
+				ps.rl = pt.RL; ps.bits = pt.bits; ps.p = per_p; ps.deep = (u32)H;
+				reduced = true; act = 0;
+				JP_TRY(run_rounds(H));                                        // h = depth .. H/2: exactly H-ordered afterwards
+				reduced = false;
+				if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
+				// every suffix takes the rank of its representative; one sort of the whole block by that key
+				u32* free_units[5]; int nf = 0;
+				for (int i = 0; i < 6; i++) if (reinterpret_cast<u32*>(b.unit[i]) != b.ISA) free_units[nf++] = reinterpret_cast<u32*>(b.unit[i]);
+				u32* k32[2] = {free_units[0], free_units[1]};
+				u32* v32[2] = {free_units[2], free_units[3]};
+				k_per_expand<<<(u32)(((size_t)n + 255) / 256), 256, 0, s>>>(b.ISA, pt.RL, pt.bits, per_p, (u32)H, (u32)n, k32[0], v32[0]); JP_LAUNCH(c);
+				const int cc = radix_sort_pairs32(k32, v32, 0, (u32)n, bit_length((u64)n_red + 1), b.rb.tile_hist, b.rb.totals, s, &c.launches);
+				if (cc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+				JP_KCHECK();
+				JP_CUDA(cudaEventRecord(c.ev[2], s));
+				k_fwd_flags<u32><<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(k32[cc], (u32)n, b.F); JP_LAUNCH(c);
+				b.SA = v32[cc];
+				b.VS = v32[cc ^ 1]; b.X = k32[cc ^ 1]; b.AP[0] = free_units[4]; b.AP[1] = k32[cc];   // (k32[cc] is dead once the flags exist)
+				// from here on: the ordinary flow at h = H, with the repeat-length keys
+				JP_TRY(per_tabs_fill(c, d_T, n, ktiles, per_p, (u32)H, pt, s));                 // bit = r(v) >= H: the suffixes pass A orders by length
+				h = H;
+				periodic = true; pass = 0;
+				keep2 = pt.keep;
+				rank_bits = bit_length(2 * (u64)n + 1);
+				st->period = (i32)per_p;
+			}
+		}
+	}
 
 	// Run bypass: worth its detection pass when a visible share of the block sits in long single-symbol runs. The histogram
 	// kernel counted the aligned 16-byte vectors of one repeated byte (every run of 31 bytes or more contains one; the
@@ -1252,9 +1534,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	// JP_BWT_FWD_BYPASS=0/1 overrides the screen.
 	RunTabs rt = {};
 	u32 R = 0, M = 0;
-	bool bypass = (u64)(u32)c.h_small[20] * 16 * 64 >= (u64)n;
-	if (const char* e = getenv("JP_BWT_FWD_BYPASS")) bypass = atoi(e) != 0;
-	const u32 ktiles = (u32)(((size_t)n + KEY_TILE - 1) / KEY_TILE);
+	bool bypass = !premode && (u64)(u32)c.h_small[20] * 16 * 64 >= (u64)n;
+	if (const char* e = getenv("JP_BWT_FWD_BYPASS")) bypass = !premode && atoi(e) != 0;
 	if (bypass) {
 		JP_TRY(run_tabs_alloc(c, n, ktiles, rt));
 		JP_CUDA(cudaMemsetAsync(rt.counters, 0, 64, s));
@@ -1267,80 +1548,65 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		R = (u32)c.h_small[14]; M = (u32)c.h_small[15];
 		if (R == 0 || R > rt.cap) bypass = false;          // nothing to place, or more runs than the tables hold: plain doubling
 	}
-	const u32 n_sorted = bypass ? (u32)n - M : (u32)n;
-	if (bypass) {
-		st->bypass_suffixes = (i32)M; st->bypass_runs = (i32)R;
-		k_run_tile_scan<<<1, 1024, 0, s>>>(rt.tile_base, ktiles, (u32)n); JP_LAUNCH(c);
-		k_fwd_keys<true><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], nullptr, 0, rt.bits, rt.tile_base); JP_LAUNCH(c);
-	} else {
-		k_fwd_keys<false><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
-		                                         rs_stride((u32)radix_tiles((size_t)n)), nullptr, nullptr); JP_LAUNCH(c);
-	}
-	JP_KCHECK();
-	JP_CUDA(cudaEventRecord(c.ev[1], s));
-	if (cudaFuncSetAttribute(k_seg_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_seg_sort_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_seg_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_LIGHT) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_seg_sort_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) { set_error_detail("k_seg_sort smem attribute"); return JP_ERR_CUDA; }
-	const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
-	if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-	JP_KCHECK();
-	JP_CUDA(cudaEventRecord(c.ev[2], s));
-
-	// The key buffers and the id buffers take new roles from here on (the keys are read one last time, for the head flags).
-	b.ISA = reinterpret_cast<u32*>(b.unit[cur ? 0 : 2]);      // first half of the other key buffer
-	b.X = reinterpret_cast<u32*>(b.unit[cur ? 1 : 3]);        // ... and its second half
-	b.AP[0] = reinterpret_cast<u32*>(b.unit[cur ? 2 : 0]);    // the sorted keys' own buffer, dead once the flags exist
-	b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
-	if (!bypass) {
-		// the sorted suffix ids ARE the suffix array
-		b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
-		k_fwd_flags<<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
-	} else {
-		// the suffix array is assembled in the other id buffer: sorted suffixes around the buckets, run suffixes inside them
-		b.SA = b.rb.v[cur ^ 1]; b.VS = b.rb.v[cur];
-		RadixBuffers lb = b.rb;
-		lb.k[0] = rt.rk[0]; lb.k[1] = rt.rk[1]; lb.v[0] = rt.rv[0]; lb.v[1] = rt.rv[1]; lb.dnext = nullptr;
-		k_run_keys<<<(R + 255) / 256, 256, 0, s>>>(d_T, (u32)n, b.meta, rt, R); JP_LAUNCH(c);
-		const int rc = radix_sort_pairs(lb, 0, R, 0, 30 + 9, s, &c.launches);
-		if (rc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-		k_run_tables<<<1, 1024, 0, s>>>(lb.k[rc], R, (u32)depth, rt); JP_LAUNCH(c);
-		k_run_lo<<<1, 256, 0, s>>>(b.rb.k[cur], n_sorted, b.meta, rt); JP_LAUNCH(c);
-		k_place_sorted<<<(n_sorted + 255) / 256, 256, 0, s>>>(b.rb.k[cur], b.rb.v[cur], n_sorted, rt, b.SA, b.F); JP_LAUNCH(c);
-		k_place_runs<<<(M + 255) / 256, 256, 0, s>>>(lb.k[rc], lb.v[rc], R, M, (u32)depth, rt, b.SA, b.F); JP_LAUNCH(c);
+	if (!premode) {
+		const u32 n_sorted = bypass ? (u32)n - M : (u32)n;
+		if (bypass) {
+			st->bypass_suffixes = (i32)M; st->bypass_runs = (i32)R;
+			k_run_tile_scan<<<1, 1024, 0, s>>>(rt.tile_base, ktiles, (u32)n); JP_LAUNCH(c);
+			k_fwd_keys<true><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], nullptr, 0, rt.bits, rt.tile_base); JP_LAUNCH(c);
+		} else {
+			k_fwd_keys<false><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
+			                                         rs_stride((u32)radix_tiles((size_t)n)), nullptr, nullptr); JP_LAUNCH(c);
+		}
 		JP_KCHECK();
-		JP_CUDA(cudaMemcpyAsync(c.h_small + 21, rt.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
+		JP_CUDA(cudaEventRecord(c.ev[1], s));
+		const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
+		if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+		JP_KCHECK();
+		JP_CUDA(cudaEventRecord(c.ev[2], s));
+
+		// The key buffers and the id buffers take new roles from here on (the keys are read one last time, for the head flags).
+		b.ISA = reinterpret_cast<u32*>(b.unit[cur ? 0 : 2]);      // first half of the other key buffer
+		b.X = reinterpret_cast<u32*>(b.unit[cur ? 1 : 3]);        // ... and its second half
+		b.AP[0] = reinterpret_cast<u32*>(b.unit[cur ? 2 : 0]);    // the sorted keys' own buffer, dead once the flags exist
+		b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
+		if (!bypass) {
+			// the sorted suffix ids ARE the suffix array
+			b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
+			k_fwd_flags<u64><<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+		} else {
+			// the suffix array is assembled in the other id buffer: sorted suffixes around the buckets, run suffixes inside them
+			b.SA = b.rb.v[cur ^ 1]; b.VS = b.rb.v[cur];
+			RadixBuffers lb = b.rb;
+			lb.k[0] = rt.rk[0]; lb.k[1] = rt.rk[1]; lb.v[0] = rt.rv[0]; lb.v[1] = rt.rv[1]; lb.dnext = nullptr;
+			k_run_keys<<<(R + 255) / 256, 256, 0, s>>>(d_T, (u32)n, b.meta, rt, R); JP_LAUNCH(c);
+			const int rc = radix_sort_pairs(lb, 0, R, 0, 30 + 9, s, &c.launches);
+			if (rc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
+			k_run_tables<<<1, 1024, 0, s>>>(lb.k[rc], R, (u32)depth, rt); JP_LAUNCH(c);
+			k_run_lo<<<1, 256, 0, s>>>(b.rb.k[cur], n_sorted, b.meta, rt); JP_LAUNCH(c);
+			k_place_sorted<<<(n_sorted + 255) / 256, 256, 0, s>>>(b.rb.k[cur], b.rb.v[cur], n_sorted, rt, b.SA, b.F); JP_LAUNCH(c);
+			k_place_runs<<<(M + 255) / 256, 256, 0, s>>>(lb.k[rc], lb.v[rc], R, M, (u32)depth, rt, b.SA, b.F); JP_LAUNCH(c);
+			JP_KCHECK();
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 21, rt.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
+		}
 	}
 	JP_CUDA(cudaMemsetAsync(b.ISA + n, 0, sizeof(u32), s));             // the empty suffix ranks below everything
-	int rank_bits = bit_length((u64)n);                                 // key2 is a rank <= n (a repeat-length key <= 2n + 1)
 	JP_TRY(group_step(c, b, nullptr, b.AP[0], (u32)n, s));
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
-	int act = 0;
-	u32 A = (u32)c.h_small[8], G = (u32)c.h_small[9];
-	u64 sectors = 2ull * (u64)n;
-	i64 h = depth;
-	int rounds = 0;
+	act = 0;
+	A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
 
 	// Periodic repeats: when most of the block is still unsorted, look for a dominant distance between group neighbours.
-	PerSkip ps; ps.rl = nullptr; ps.bits = nullptr; ps.T = d_T; ps.p = 1; ps.first = 0;
-	bool periodic = false;
-	int pass = 0;                                                       // 0: pass A still to come, 1: pass B next (same h), 2: both done
-	i64 h_a = 0;                                                        // the h of pass A: first h >= p
-	size_t keep2 = 0;                                                   // bytes at the start of the second arena that later growth must keep
 	const u32 shared_levels = bypass ? (u32)c.h_small[21] : 0;
 	bool run_jumps = shared_levels >= 2048;                              // worth a second detection pass
 	if (const char* e = getenv("JP_BWT_FWD_RUNJUMP")) run_jumps = atoi(e) != 0 && shared_levels > 0;
+	if (!premode)
 	{
 		bool look = (u64)A * 4 >= (u64)n * 3 && n >= (1 << 16);
 		if (const char* e = getenv("JP_BWT_FWD_PERIODIC")) look = atoi(e) != 0 && A >= 2 * PER_SAMPLE;
 		if (look) {
-			size_t off = 0;
-			auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
-			const size_t o_bits = take(((size_t)n / 32 + 2) * 4), o_tf = take((size_t)ktiles * 4), o_tn = take((size_t)ktiles * 4), o_rl = take((size_t)n * 4),
-			             o_hist = take((size_t)PER_MAXP * 4), o_ct = take(64);
-			JP_TRY(arena2_reserve(c, off));                               // (the run bypass tables, if any, are dead by now)
-			u8* a2 = c.arena2.base;
-			u32* hist = (u32*)(a2 + o_hist); u32* ct = (u32*)(a2 + o_ct);
+			JP_TRY(arena2_reserve(c, (size_t)PER_MAXP * 4 + 256));          // (the run bypass tables, if any, are dead by now)
+			u32* hist = (u32*)c.arena2.base; u32* ct = hist + PER_MAXP;
 			JP_CUDA(cudaMemsetAsync(hist, 0, (size_t)PER_MAXP * 4 + 64, s));
 			const u32 samples = (A + PER_SAMPLE - 1) / PER_SAMPLE;
 			k_per_sample<<<(samples + 255) / 256, 256, 0, s>>>(b.AP[0], b.SA, A, hist); JP_LAUNCH(c);
@@ -1353,15 +1619,10 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			while (h_a < (i64)p) h_a *= 2;
 			if (p >= 1 && (u64)hits * PER_SAMPLE * 2 >= (u64)A && h_a * 4 <= (i64)n) {
 				periodic = true;
-				RunTabs pt = {};
-				pt.bits = (u32*)(a2 + o_bits); pt.tile_first = (u32*)(a2 + o_tf); pt.tile_next = (u32*)(a2 + o_tn); pt.counters = ct;
-				u32* RL = (u32*)(a2 + o_rl);
-				k_run_first<<<ktiles, 256, 0, s>>>(d_T, (u32)n, p, pt.tile_first); JP_LAUNCH(c);
-				k_run_scan<<<1, 1024, 0, s>>>(pt.tile_first, ktiles, pt.tile_next); JP_LAUNCH(c);
-				k_run_fill<false><<<ktiles, 256, 0, s>>>(d_T, (u32)n, p, pt.tile_next, (u32)h_a, pt, RL); JP_LAUNCH(c);
-				JP_KCHECK();
-				ps.rl = RL; ps.bits = pt.bits; ps.p = p;
-				keep2 = o_hist;                                           // bits, tile tables and RL stay; the histogram is dead
+				JP_TRY(per_tabs_alloc(c, n, ktiles, pt));                     // repeat lengths: 4.1 N, only now that they are needed
+				JP_TRY(per_tabs_fill(c, d_T, n, ktiles, p, (u32)h_a, pt, s));
+				ps.rl = pt.RL; ps.bits = pt.bits; ps.p = p;
+				keep2 = pt.keep;
 				rank_bits = bit_length(2 * (u64)n + 1);
 				st->period = (i32)p;
 			}
@@ -1373,117 +1634,14 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		// (class, run length) -- the placement did what pass A does -- so the jump keys of pass B apply from the first round on:
 		// a run suffix with r >= h takes the rank of the suffix right after its run, and such a level is resolved as soon
 		// as the followers differ instead of after log2(run length / depth) rounds.
-		size_t off = 0;
-		auto take = [&](size_t bytes) { const size_t o = off; off += Arena::align(bytes); return o; };
-		const size_t o_bits = take(((size_t)n / 32 + 2) * 4), o_tf = take((size_t)ktiles * 4), o_tn = take((size_t)ktiles * 4), o_rl = take((size_t)n * 4), o_ct = take(64);
-		JP_TRY(arena2_reserve(c, off));                                   // (the bypass tables are dead: everything is placed)
-		u8* a2 = c.arena2.base;
-		RunTabs pt = {};
-		pt.bits = (u32*)(a2 + o_bits); pt.tile_first = (u32*)(a2 + o_tf); pt.tile_next = (u32*)(a2 + o_tn); pt.counters = (u32*)(a2 + o_ct);
-		u32* RL = (u32*)(a2 + o_rl);
-		JP_CUDA(cudaMemsetAsync(pt.counters, 0, 64, s));
-		k_run_first<<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, pt.tile_first); JP_LAUNCH(c);
-		k_run_scan<<<1, 1024, 0, s>>>(pt.tile_first, ktiles, pt.tile_next); JP_LAUNCH(c);
-		k_run_fill<false><<<ktiles, 256, 0, s>>>(d_T, (u32)n, 1u, pt.tile_next, (u32)depth, pt, RL); JP_LAUNCH(c);
-		JP_KCHECK();
-		ps.rl = RL; ps.bits = pt.bits; ps.p = 1;
+		JP_TRY(per_tabs_alloc(c, n, ktiles, pt));                         // (the bypass tables are dead: everything is placed)
+		JP_TRY(per_tabs_fill(c, d_T, n, ktiles, 1u, (u32)depth, pt, s));
+		ps.rl = pt.RL; ps.bits = pt.bits; ps.p = 1;
 		periodic = true; pass = 1; h_a = depth;
-		keep2 = o_ct;
+		keep2 = pt.keep;
 		st->period = 1;
 	}
-	const bool trace_rounds = getenv("JP_BWT_TRACE_ROUNDS") != nullptr;      // one stderr line per doubling round (host wall time)
-	double t_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-	std::vector<u32> h_off;
-	while (A > 0) {
-		if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
-		if (rounds >= JP_BWT_MAX_ROUNDS || h > (i64)n) { set_error_detail("doubling stuck: round %d h=%lld active=%u", rounds, (long long)h, A); return JP_ERR_INTERNAL; }
-		st->active_fraction[rounds] = (float)((double)A / (double)n);
-		sectors += 2ull * A;
-		double large_frac_now = 0.0;
-		const u32* AP = b.AP[act];
-		const bool use_ps = periodic && h >= h_a;                        // the repeat-length keys apply from the first h >= p on
-		ps.first = (use_ps && pass == 0) ? 1u : 0u;
-		// short groups: fused gather + warp-level rank refinement in shared memory; longer ones are queued for the
-		// shared-memory radix kernel; groups longer than a window are reported for the large-group route
-		const u32 nwin = (A + SG_WIN - 1) / SG_WIN;
-		JP_CUDA(cudaMemsetAsync(b.counters + 2, 0, 4 * sizeof(u32), s));
-		if (use_ps) k_seg_sort<true><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
-		else k_seg_sort<false><<<nwin, SG_THREADS, SG_SMEM_LIGHT, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, b.F, b.counters, b.queue, b.win_first, b.win_large, b.err, ps);
-		JP_LAUNCH(c);
-		JP_KCHECK();
-		JP_CUDA(cudaMemcpyAsync(c.h_small + 10, b.counters + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-		JP_CUDA(cudaStreamSynchronize(s));
-		const bool large = c.h_small[10] != 0;
-		const u32 queued = (u32)c.h_small[11];
-		if (queued) {
-			if (use_ps) k_seg_sort_radix<true><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
-			else k_seg_sort_radix<false><<<queued, SG_THREADS, SG_SMEM, s>>>(AP, b.SA, A, b.ISA, (u32)h, (u32)n, rank_bits, b.F, b.queue, b.err, ps);
-			JP_LAUNCH(c);
-			JP_KCHECK();
-			st->radix_tiles += (i32)queued;
-		}
-		if (large) {
-			k_large_collect<<<1, 1024, 0, s>>>(b.win_first, b.win_large, nwin, A, b.lg_head, b.lg_off, b.counters); JP_LAUNCH(c);
-			JP_KCHECK();
-			JP_CUDA(cudaMemcpyAsync(c.h_small + 12, b.counters + 4, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-			JP_CUDA(cudaStreamSynchronize(s));
-			const u32 ng = (u32)c.h_small[12], total = (u32)c.h_small[13];
-			st->large_fraction += (float)((double)total / (double)n);   // share of the block on the large-group route, summed over rounds
-			large_frac_now = (double)total / (double)A;
-			if (ng == 0 || total == 0 || total > A) { set_error_detail("large-group list inconsistent: %u groups, %u suffixes, %u active", ng, total, A); return JP_ERR_INTERNAL; }
-			// Scratch of the sort: the spare unit, the staging unit and the idle active buffer hold (8 + 8 + 2 x 4) bytes for
-			// up to N/2 suffixes. More than that (blocks that are mostly long repeats) goes through in batches of whole groups;
-			// a single group beyond N/2 falls back on the second arena.
-			const u32 cap = (u32)(b.usz / 8);
-			if (total > cap) {
-				h_off.resize((size_t)ng + 1);
-				JP_CUDA(cudaMemcpyAsync(h_off.data(), b.lg_off, ((size_t)ng + 1) * 4, cudaMemcpyDeviceToHost, s));
-				JP_CUDA(cudaStreamSynchronize(s));
-			}
-			for (u32 g0 = 0; g0 < ng;) {
-				u32 g1 = ng, x0 = 0, count = total;
-				if (total > cap) {
-					g1 = g0 + 1;
-					while (g1 < ng && h_off[g1 + 1] - h_off[g0] <= cap) g1++;
-					x0 = h_off[g0]; count = h_off[g1] - x0;
-				}
-				RadixBuffers lb = b.rb;
-				lb.dnext = nullptr;                         // the flag bytes of this round are live in b.F
-				if (count <= cap) {
-					lb.k[0] = reinterpret_cast<u64*>(b.X); lb.k[1] = reinterpret_cast<u64*>(b.VS);
-					lb.v[0] = b.AP[act ^ 1]; lb.v[1] = b.AP[act ^ 1] + b.usz / 8;
-				} else {
-					const size_t T8 = Arena::align((size_t)count * 8), T4 = Arena::align((size_t)count * 4), base = Arena::align(keep2);
-					JP_TRY(arena2_reserve(c, base + 2 * T8 + 2 * T4, keep2));
-					u8* a2 = c.arena2.base;
-					if (periodic) { ps.bits = (const u32*)a2; ps.rl = (const u32*)(a2 + ((const u8*)ps.rl - (const u8*)ps.bits)); }
-					lb.k[0] = reinterpret_cast<u64*>(a2 + base); lb.k[1] = reinterpret_cast<u64*>(a2 + base + T8);
-					lb.v[0] = reinterpret_cast<u32*>(a2 + base + 2 * T8); lb.v[1] = reinterpret_cast<u32*>(a2 + base + 2 * T8 + T4);
-				}
-				if (use_ps) k_large_extract<true><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
-				else k_large_extract<false><<<(count + 255) / 256, 256, 0, s>>>(AP, b.SA, b.ISA, (u32)h, (u32)n, rank_bits, b.lg_head, b.lg_off, ng, g0, x0, count, lb.k[0], lb.v[0], b.err, ps);
-				JP_LAUNCH(c);
-				const int key_bits = rank_bits + bit_length((u64)(g1 - g0 - 1));
-				const int lc = radix_sort_pairs(lb, 0, count, 0, key_bits, s, &c.launches);
-				if (lc < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
-				k_large_writeback<<<(count + 255) / 256, 256, 0, s>>>(lb.k[lc], lb.v[lc], rank_bits, b.lg_head, b.lg_off, g0, x0, count, AP, b.SA, b.F); JP_LAUNCH(c);
-				JP_KCHECK();
-				g0 = g1;
-			}
-		}
-		JP_TRY(group_step(c, b, AP, b.AP[act ^ 1], A, s));
-		if (trace_rounds) {
-			const double t1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-			fprintf(stderr, "[jp_bwt round] %d h=%lld%s active=%u groups=%u -> active=%u groups=%u large_frac=%.4f %.3f ms\n", rounds, (long long)h,
-			        use_ps ? (pass == 0 ? " (repeat lengths)" : " (repeat jumps)") : "", A, G, (u32)c.h_small[8], (u32)c.h_small[9], large_frac_now, t1 - t_round);
-			t_round = t1;
-		}
-		act ^= 1;
-		A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
-		if (use_ps && pass == 0) pass = 1;                               // pass B repeats this h
-		else { h *= 2; if (use_ps) pass = 2; }
-		rounds++;
-	}
+	JP_TRY(run_rounds((i64)1 << 40));
 	if (c.h_small[0] != 0) return map_dev_err(c.h_small[0]);
 	JP_CUDA(cudaEventRecord(c.ev[4], s));
 	st->rounds = rounds;

@@ -402,6 +402,25 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 	return cur;
 }
 
+// LSD sort of (32-bit key, 32-bit value) pairs by key bits [0, bits): k[cur], v[cur] -> returns the index of the buffers
+// holding the result (or a negative error code). Used where ranks, not text prefixes, are the keys.
+inline int radix_sort_pairs32(u32* const k[2], u32* const v[2], int cur, u32 n, int bits, u32* tile_hist, u32* totals, cudaStream_t s, int* launches)
+{
+	if (n == 0) return cur;
+	const size_t smem = (size_t)RS_TILE * (4 + 4);
+	if (cudaFuncSetAttribute(k_rs_scatter<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
+	for (int shift = 0; shift < bits; shift += 8) {
+		k_rs_hist<u32><<<tiles, RS_THREADS, 0, s>>>(k[cur], n, shift, tile_hist, stride);
+		k_rs_totals<<<256, 256, 0, s>>>(tile_hist, tiles, stride, totals);
+		k_rs_scan<<<256, 256, 0, s>>>(tile_hist, tiles, stride, totals);
+		k_rs_scatter<u32><<<tiles, RS_THREADS, smem, s>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], tile_hist, stride, n, shift);
+		*launches += 4;
+		cur ^= 1;
+	}
+	return cur;
+}
+
 // One stable 8-bit partition pass over (32-bit key, 32-bit value) pairs: (kin, vin) -> (kout, vout) ordered by
 // digit (key >> shift) & 255. Used to bucket (suffix, rank) pairs by ISA region before they are scattered.
 inline int radix_partition_u32(const u32* kin, const u32* vin, u32* kout, u32* vout, u32 n, int shift,

@@ -196,6 +196,31 @@ def test_emulated_forward_with_periodic_repeats(emu, orc, name):
         assert rounds["01"] < rounds["00"], rounds
 
 
+REDUCED_CASES = {"repetitive_200k": lambda orc: orc.gen("repetitive", 200000, 3), "period_300_binary": lambda orc: _periodic(160000, 300, 2, 6, 4),
+                 "period_60": lambda orc: _periodic(150000, 60, 5, 10, 3), "period_5000": lambda orc: _periodic(180000, 5000, 4, 3, 8),
+                 "period_7_clean": lambda orc: _periodic(140000, 7, 3, 0, 2), "not_periodic": lambda orc: orc.gen("markov2", 140000, 1),
+                 "half_periodic": lambda orc: np.concatenate([_periodic(100000, 97, 4, 4, 5), orc.gen("markov2", 60000, 2)])}
+
+
+@pytest.mark.parametrize("name", sorted(REDUCED_CASES))
+def test_emulated_forward_of_periodic_block_through_representatives(emu, orc, name):
+    """A block whose period shows in the text before the sort is sorted through one representative per stretch and phase
+    (bwt_forward.cu, "periodic blocks are sorted through their representatives"); the probe is forced on (blocks under 1 Mi
+    do not look by default)."""
+    T = REDUCED_CASES[name](orc)
+    want = orc.forward(T, "port", prefill=0x5C)
+    saved = os.environ.get("JP_BWT_FWD_REDUCED")
+    os.environ["JP_BWT_FWD_REDUCED"] = "1"
+    try:
+        rc, got, rounds, _ = emu.forward(T)
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_REDUCED", None)
+        else:
+            os.environ["JP_BWT_FWD_REDUCED"] = saved
+    assert rc == 0 and (got == want).all()
+
+
 @pytest.mark.parametrize("kind,n,seed", [("kat_extremes", 2, 0), ("uniform", 3, 1), ("alla", 1000, 0), ("markov2", 3000, 2), ("repetitive", 5000, 3)])
 def test_emulated_suffix_array(emu, orc, kind, n, seed):
     """jp::debug_suffix_array (the sorter behind jp_bwt_suffix_array / the -m2 shim) against a brute-force sort."""

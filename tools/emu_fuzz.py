@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 import oracle  # noqa: E402
 import simt  # noqa: E402
 
-SWITCHES = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2", "JP_BWT_INV_SINGLE", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM")
+SWITCHES = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP", "JP_BWT_FWD_REDUCED", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2", "JP_BWT_INV_SINGLE", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM")
 
 
 def block(rng, n):
