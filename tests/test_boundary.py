@@ -22,7 +22,7 @@ def jp():
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "jp_bwt.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(jp_bwt_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(jp_(?:bwt|src)_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_header_symbols_all_exported(jp):

@@ -163,9 +163,9 @@ def _periodic(n, p, sig, defects, seed):
     return T
 
 
-PERIODIC_CASES = {"repetitive_70k": lambda orc: orc.gen("repetitive", 70000, 3), "period_3": lambda orc: _periodic(30000, 3, 4, 5, 1),
-                  "period_7_clean": lambda orc: _periodic(50000, 7, 3, 0, 2), "period_60": lambda orc: _periodic(40000, 60, 5, 10, 3),
-                  "period_300_binary": lambda orc: _periodic(90000, 300, 2, 4, 4), "period_2": lambda orc: _periodic(20000, 2, 2, 3, 6),
+PERIODIC_CASES = {"repetitive_70k": lambda orc: orc.gen("repetitive", 70000, 3), "period_3": lambda orc: _periodic(12000, 3, 4, 5, 1),
+                  "period_7_clean": lambda orc: _periodic(15000, 7, 3, 0, 2), "period_60": lambda orc: _periodic(40000, 60, 5, 10, 3),
+                  "period_300_binary": lambda orc: _periodic(90000, 300, 2, 4, 4), "period_2": lambda orc: _periodic(9000, 2, 2, 3, 6),
                   "runs_in_a_period": lambda orc: np.tile(np.concatenate([np.zeros(70, np.uint8), np.array([1, 2, 1], np.uint8)]), 200),
                   "not_periodic": lambda orc: orc.gen("markov2", 30000, 1)}
 
