@@ -426,8 +426,10 @@ __global__ void __launch_bounds__(256) k_place_sorted(const u64* __restrict__ K,
 }
 
 // every run suffix computes its own place
+// A level that only one run reaches is a singleton for good: its rank is written here (consecutive suffixes, consecutive
+// positions: coalesced) and its flag says so (F = 2), so that the grouping step neither reads nor ranks it again.
 __global__ void __launch_bounds__(256) k_place_runs(const u64* __restrict__ sk, const u32* __restrict__ sv, u32 R, u32 M, u32 depth, RunTabs rt,
-                                                    u32* __restrict__ SA, u8* __restrict__ F)
+                                                    u32* __restrict__ SA, u8* __restrict__ F, u32* __restrict__ ISA)
 {
 	const u32 u = blockIdx.x * 256 + threadIdx.x;
 	u32 q = 0;
@@ -449,7 +451,8 @@ __global__ void __launch_bounds__(256) k_place_runs(const u64* __restrict__ sk, 
 		const u32 Mb = rt.PS[be] - rt.PS[bs];
 		const u32 pos = (b & 1u) == 0 ? rt.lo[b] + off + idx : rt.lo[b] + Mb - off - q + idx;
 		SA[pos] = v;
-		F[pos] = idx == 0 ? 1 : 0;
+		if (q == 1) { F[pos] = 2; ISA[v] = pos + 1; }
+		else F[pos] = idx == 0 ? 1 : 0;
 	}
 	const u32 shared = __popc(__ballot_sync(0xffffffffu, q > 1));     // run suffixes in levels that several runs reach
 	if (shared && (threadIdx.x & 31) == 0) atomicAdd(&rt.counters[2], shared);
@@ -561,9 +564,11 @@ __global__ void __launch_bounds__(1024) k_grp_scan_tiles(GAgg* __restrict__ agg,
 //   AP == nullptr: the slots are the positions 0..A-1 themselves (the step after the initial sort).
 //   R  != nullptr: ranks leave in slot order (and the suffix ids in VS, if given) for k_isa_scatter to place; R may be
 //                  AP itself -- every thread reads its own slots before it writes them.
+//   F[j] == 2: a singleton whose rank is already in ISA (run bypass): not read, not ranked; a tile made of nothing else
+//                  says so in tile_final[tile] and k_isa_scatter skips it (R = 0 marks such slots in mixed tiles).
 __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u8* __restrict__ F, const u32* AP, const u32* __restrict__ SA, u32 A,
                                                           const GAgg* __restrict__ agg, u32* __restrict__ ISA, u32* R, u32* __restrict__ VS,
-                                                          u32* __restrict__ APn)
+                                                          u32* __restrict__ APn, u32* __restrict__ tile_final)
 {
 	__shared__ i32 wmh[GS_SUB][8];
 	__shared__ u32 wpk[GS_SUB][8];
@@ -571,18 +576,22 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u8* __restrict__
 	const u32 base = blockIdx.x * GS_TILE;
 	const GAgg carry0 = agg[blockIdx.x];
 
-	u32 v[GS_SUB], p[GS_SUB], fl[GS_SUB];     // fl: bit0 valid, bit1 head, bit2 survivor, bit3 surviving head
+	u32 v[GS_SUB], p[GS_SUB], fl[GS_SUB];     // fl: bit0 valid, bit1 head, bit2 survivor, bit3 surviving head, bit4 final (rank already placed)
+	int all_final = 1;
 	#pragma unroll
 	for (int s = 0; s < GS_SUB; s++) {
 		const u32 j = base + s * GS_THREADS + t;
 		v[s] = 0; p[s] = 0; fl[s] = 0;
 		if (j < A) {
-			const bool head = F[j] != 0, nhead = (j + 1 == A) || (F[j + 1] != 0);
-			fl[s] = 1u | (head ? 2u : 0u) | (!(head && nhead) ? 4u : 0u) | ((head && !nhead) ? 8u : 0u);
+			const u32 f = F[j];
+			const bool head = f != 0, nhead = (j + 1 == A) || (F[j + 1] != 0);
+			fl[s] = 1u | (head ? 2u : 0u) | (!(head && nhead) ? 4u : 0u) | ((head && !nhead) ? 8u : 0u) | (f == 2 ? 16u : 0u);
 			p[s] = AP ? (AP[j] & AP_POS) : j;
-			v[s] = SA[p[s]];
+			if (f != 2) { v[s] = SA[p[s]]; all_final = 0; }
 		}
 	}
+	all_final = __syncthreads_and(all_final);
+	if (threadIdx.x == 0 && tile_final) tile_final[blockIdx.x] = (u32)all_final;
 	i32 imh[GS_SUB]; u32 ipk[GS_SUB];
 	#pragma unroll
 	for (int s = 0; s < GS_SUB; s++) {
@@ -607,7 +616,8 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u8* __restrict__
 			const i32 fmh = max(imh[s], pm);
 			const u32 fpk = ipk[s] + pp;
 			const u32 j = base + s * GS_THREADS + t;
-			if (R) { R[j] = (u32)fmh + 1u; if (VS) VS[j] = v[s]; }      // ranks leave in slot order; k_isa_scatter places them
+			if (fl[s] & 16u) { if (R) R[j] = 0; }
+			else if (R) { R[j] = (u32)fmh + 1u; if (VS) VS[j] = v[s]; } // ranks leave in slot order; k_isa_scatter places them
 			else ISA[v[s]] = (u32)fmh + 1u;
 			if (fl[s] & 4u) APn[carry0.ns + (fpk & 0xffffu) - 1] = p[s] | ((fl[s] & 2u) ? AP_HEAD : 0u);
 		}
@@ -621,9 +631,10 @@ __global__ void __launch_bounds__(GS_THREADS) k_grp_apply(const u8* __restrict__
 // that fall in its region, so the sectors fill up in L2 and go to DRAM once, complete. Blocks are ordered by
 // region, so the passes follow each other inside one launch.
 __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, const u32* __restrict__ R, u32 A, u32* __restrict__ ISA,
-                                                     int region_log2, u32 tiles)
+                                                     int region_log2, u32 tiles, const u32* __restrict__ tile_final)
 {
 	const u32 region = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+	if (tile_final && tile_final[tile]) return;                 // nothing but ranks that are already in place
 	const u32 base = tile * 2048 + threadIdx.x;
 	u32 v[8], r[8];
 	#pragma unroll
@@ -633,7 +644,7 @@ __global__ void __launch_bounds__(256) k_isa_scatter(const u32* __restrict__ V, 
 		if (j < A) { v[i] = __ldcs(V + j); r[i] = __ldcs(R + j); }
 	}
 	#pragma unroll
-	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && (region_log2 >= 32 || (v[i] >> region_log2) == region)) ISA[v[i]] = r[i];
+	for (int i = 0; i < 8; i++) if (v[i] != 0xffffffffu && r[i] != 0 && (region_log2 >= 32 || (v[i] >> region_log2) == region)) ISA[v[i]] = r[i];
 }
 
 // ---- 5. doubling rounds ----------------------------------------------------------------------------------
@@ -730,24 +741,24 @@ __global__ void __launch_bounds__(1024) k_per_pick(const u32* __restrict__ hist,
 // 67 M suffixes (6.2 ms each) become six rounds over 4 M, and the eight 12-byte radix passes of the initial sort three
 // 8-byte ones. The period is found in the text itself: for 64 sampled positions, the distance to the next occurrence
 // of the 32 bytes that follow; if half of the samples agree, that distance is p (0.02 ms on a block without a period).
-constexpr u32 PROBE_SAMPLES = 64, PROBE_WIN = 32;
+constexpr u32 PROBE_SAMPLES = 64, PROBE_WIN = 32, PROBE_MAXP = 16384;   // (longer periods are still found after the initial step)
 // one block per sample: thread t tries the distances t + 1, t + 257, ...; the block stops at the first round that has a hit
 __global__ void __launch_bounds__(256) k_per_probe(const u8* __restrict__ T, u32 n, u32* __restrict__ out)
 {
 	__shared__ u32 s_found;
 	const u32 t = threadIdx.x, sample = blockIdx.x;
-	const u32 span = PER_MAXP + PROBE_WIN;
+	const u32 span = PROBE_MAXP + PROBE_WIN;
 	if (t == 0) s_found = 0xffffffffu;
 	__syncthreads();
 	if (n > 2 * span) {
 		const u32 a = (u32)(((u64)sample * (u64)(n - span - 1)) / PROBE_SAMPLES);
 		const u32 w0 = (u32)T[a] | ((u32)T[a + 1] << 8) | ((u32)T[a + 2] << 16) | ((u32)T[a + 3] << 24);
-		for (u32 d0 = 1; d0 < PER_MAXP; d0 += 2048) {                  // eight distances per thread between two barriers
+		for (u32 d0 = 1; d0 < PROBE_MAXP; d0 += 2048) {                  // eight distances per thread between two barriers
 			bool any = false;
 			#pragma unroll 2
 			for (u32 k8 = 0; k8 < 8; k8++) {
 				const u32 d = d0 + k8 * 256 + t;
-				if (d >= PER_MAXP) break;
+				if (d >= PROBE_MAXP) break;
 				const u8* q = T + a + d;
 				if (((u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24)) != w0) continue;
 				bool hit = true;
@@ -1231,7 +1242,7 @@ static int place_ranks(Ctx& c, FwdBuffers& b, const u32* V, const u32* R, u32 A,
 	if (regions <= 4 || regions > 256) {
 		// few regions: stream the slots once per region and keep the ranks that fall in it
 		const u32 stiles = (A + 2047) / 2048;
-		k_isa_scatter<<<regions * stiles, 256, 0, s>>>(V, R, A, b.ISA, b.isa_region_log2, stiles); JP_LAUNCH(c);
+		k_isa_scatter<<<regions * stiles, 256, 0, s>>>(V, R, A, b.ISA, b.isa_region_log2, stiles, b.queue); JP_LAUNCH(c);
 		return JP_OK;
 	}
 	// many regions (blocks over 64 MiB): one radix partition pass buckets the (suffix, rank) pairs by region, then a
@@ -1240,7 +1251,7 @@ static int place_ranks(Ctx& c, FwdBuffers& b, const u32* V, const u32* R, u32 A,
 		const u32 cnt = std::min(pcap, A - off);
 		if (radix_partition_u32(V + off, R + off, pv, pr, cnt, b.isa_region_log2, b.rb.tile_hist, b.rb.totals, s, &c.launches) != 0) { set_error_detail("radix partition setup failed"); return JP_ERR_CUDA; }
 		const u32 stiles = (cnt + 2047) / 2048;
-		k_isa_scatter<<<stiles, 256, 0, s>>>(pv, pr, cnt, b.ISA, 32, stiles); JP_LAUNCH(c);
+		k_isa_scatter<<<stiles, 256, 0, s>>>(pv, pr, cnt, b.ISA, 32, stiles, nullptr); JP_LAUNCH(c);
 	}
 	return JP_OK;
 }
@@ -1255,15 +1266,16 @@ static int group_step(Ctx& c, FwdBuffers& b, const u32* APin, u32* APout, u32 A,
 	// small active sets (and the A/B switch region_log2 <= 0) scatter straight from the apply kernel
 	const u32 stage_min = getenv("JP_BWT_ISA_STAGE_MIN") ? (u32)atol(getenv("JP_BWT_ISA_STAGE_MIN")) : (1u << 20);   // (tests lower it)
 	const bool staged = b.isa_region_log2 > 0 && A > stage_min;
-	if (!staged) { k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, nullptr, nullptr, APout); JP_LAUNCH(c); }
+	// (b.queue, idle between the sorting kernels of a round, carries the per-tile "all ranks already placed" words)
+	if (!staged) { k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, nullptr, nullptr, APout, b.queue); JP_LAUNCH(c); }
 	else if (APin == nullptr) {
 		// initial step: the suffix ids are SA itself; ranks go to the spare unit; VS and the second active buffer are free
-		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, nullptr, b.SA, A, b.agg, b.ISA, b.X, nullptr, APout); JP_LAUNCH(c);
+		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, nullptr, b.SA, A, b.agg, b.ISA, b.X, nullptr, APout, b.queue); JP_LAUNCH(c);
 		JP_TRY(place_ranks(c, b, b.SA, b.X, A, b.VS, APout == b.AP[0] ? b.AP[1] : b.AP[0], (u32)(b.usz / 4), s));
 	} else {
 		// a round: ranks overwrite the (dead) input slots, suffix ids are staged in VS; the spare unit holds the bucketed pairs
 		u32* R = const_cast<u32*>(APin);
-		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, R, b.VS, APout); JP_LAUNCH(c);
+		k_grp_apply<<<tiles, GS_THREADS, 0, s>>>(b.F, APin, b.SA, A, b.agg, b.ISA, R, b.VS, APout, b.queue); JP_LAUNCH(c);
 		const u32 half = (u32)(b.usz / 8);
 		JP_TRY(place_ranks(c, b, b.VS, R, A, b.X, b.X + half, half, s));
 	}
@@ -1337,11 +1349,12 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	k_fwd_codes<<<1, 256, 0, s>>>(b.meta); JP_LAUNCH(c);
 	// period probe (sorting a periodic block through its representatives): the samples land in the radix histogram area
 	int want_probe = n >= (1 << 20) ? 1 : 0;
-	if (const char* e = getenv("JP_BWT_FWD_REDUCED")) want_probe = atoi(e) != 0 && (u32)n > 2 * (PER_MAXP + PROBE_WIN) ? 1 : 0;
+	if (const char* e = getenv("JP_BWT_FWD_REDUCED")) want_probe = atoi(e) != 0 && (u32)n > 2 * (PROBE_MAXP + PROBE_WIN) ? 1 : 0;
 	if (want_probe) { k_per_probe<<<PROBE_SAMPLES, 256, 0, s>>>(d_T, (u32)n, b.rb.tile_hist); JP_LAUNCH(c); }
 	JP_KCHECK();
-	u32 h_probe[PROBE_SAMPLES];
-	if (want_probe) JP_CUDA(cudaMemcpyAsync(h_probe, b.rb.tile_hist, sizeof(h_probe), cudaMemcpyDeviceToHost, s));
+	static_assert(PROBE_SAMPLES <= 192, "the samples are read back through the context's pinned words");
+	u32* h_probe = reinterpret_cast<u32*>(c.h_small + 64);
+	if (want_probe) JP_CUDA(cudaMemcpyAsync(h_probe, b.rb.tile_hist, PROBE_SAMPLES * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	JP_CUDA(cudaMemcpyAsync(c.h_small + 16, &b.meta->sigma, 5 * sizeof(i32), cudaMemcpyDeviceToHost, s)); // sigma, bits, depth, key_bits, eq4
 	JP_CUDA(cudaStreamSynchronize(s));
 	const int bits = c.h_small[17], depth = c.h_small[18], key_bits0 = c.h_small[19];
@@ -1585,7 +1598,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			k_run_tables<<<1, 1024, 0, s>>>(lb.k[rc], R, (u32)depth, rt); JP_LAUNCH(c);
 			k_run_lo<<<1, 256, 0, s>>>(b.rb.k[cur], n_sorted, b.meta, rt); JP_LAUNCH(c);
 			k_place_sorted<<<(n_sorted + 255) / 256, 256, 0, s>>>(b.rb.k[cur], b.rb.v[cur], n_sorted, rt, b.SA, b.F); JP_LAUNCH(c);
-			k_place_runs<<<(M + 255) / 256, 256, 0, s>>>(lb.k[rc], lb.v[rc], R, M, (u32)depth, rt, b.SA, b.F); JP_LAUNCH(c);
+				k_place_runs<<<(M + 255) / 256, 256, 0, s>>>(lb.k[rc], lb.v[rc], R, M, (u32)depth, rt, b.SA, b.F, b.ISA); JP_LAUNCH(c);
 			JP_KCHECK();
 			JP_CUDA(cudaMemcpyAsync(c.h_small + 21, rt.counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
 		}

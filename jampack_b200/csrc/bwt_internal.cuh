@@ -25,7 +25,7 @@ struct Ctx {
 	cudaStream_t own_stream = nullptr;
 	Arena        arena;
 	Arena        arena2;              // second, lazily grown allocation: scratch only unusual blocks need (forward: sorting over-long groups)
-	int*         h_small = nullptr;   // pinned: error flag + counters read back per round (64 ints)
+	int*         h_small = nullptr;   // pinned: error flag + counters read back per round ([0..64)), period probe samples ([64..256))
 	u8*          h_stage[2] = {nullptr, nullptr}; // pinned staging for pageable host blocks
 	size_t       h_stage_cap = 0;
 	u8*          d_in = nullptr;      // device copies of the caller's host blocks (host entry points)

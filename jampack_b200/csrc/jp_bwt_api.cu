@@ -224,7 +224,7 @@ static int create_ctx(int device, Ctx** out)
 		if ((v == 32 || v == 64 || v == 128) && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) cudaGetLastError();
 	}
 	JP_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-	JP_CUDA(cudaMallocHost(&c->h_small, 64 * sizeof(int)));
+	JP_CUDA(cudaMallocHost(&c->h_small, 256 * sizeof(int)));
 	for (auto& e : c->ev) JP_CUDA(cudaEventCreate(&e));
 	JP_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
 	c->busy = true;

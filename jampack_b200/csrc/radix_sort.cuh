@@ -11,7 +11,10 @@
 
 namespace jp {
 
-constexpr int RS_THREADS = 256;
+#ifndef RS_THREADS_CFG
+#define RS_THREADS_CFG 256
+#endif
+constexpr int RS_THREADS = RS_THREADS_CFG;          // 256 (16 pairs per thread) measured best; 512 x 8 is the A/B variant
 constexpr int RS_WARPS   = RS_THREADS / 32;
 #ifndef RS_ITEMS_CFG
 #define RS_ITEMS_CFG 16
@@ -54,10 +57,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ ke
 		} else if (ok) atomicAdd(&hw[d], 1u);
 	}
 	__syncthreads();
-	u32 s = 0;
-	#pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
-	tile_hist[(size_t)t * stride + blockIdx.x] = s;
+	if (t < 256) {
+		u32 s = 0;
+		#pragma unroll
+		for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
+		tile_hist[(size_t)t * stride + blockIdx.x] = s;
+	}
 }
 
 // The same tile histogram from a one-byte-per-key digit array. Every scatter pass leaves such an array for the NEXT
@@ -87,10 +92,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist_bytes(const u8* __restri
 		for (u32 k = p; k < n && k < p + 16; k++) atomicAdd(&hw[digits[k]], 1u);
 	}
 	__syncthreads();
-	u32 s = 0;
-	#pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
-	tile_hist[(size_t)t * stride + blockIdx.x] = s;
+	if (t < 256) {
+		u32 s = 0;
+		#pragma unroll
+		for (int k = 0; k < RS_WARPS; k++) s += h[k][t];
+		tile_hist[(size_t)t * stride + blockIdx.x] = s;
+	}
 }
 
 // block d: total of digit d over all tiles (one coalesced row)
@@ -186,12 +193,16 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 
 	// digit t: exclusive scan over warps, then over digits
 	u32 run = 0;
-	#pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+	if (t < 256) {
+		#pragma unroll
+		for (int k = 0; k < RS_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
+	}
 	u32 total;
 	const u32 inc = block_incl_sum(run, ws, &total);
-	bin_start[t] = inc - run;
-	g_off[t] = tile_off[(size_t)t * stride + blockIdx.x] - (inc - run);
+	if (t < 256) {
+		bin_start[t] = inc - run;
+		g_off[t] = tile_off[(size_t)t * stride + blockIdx.x] - (inc - run);
+	}
 	__syncthreads();
 
 	#pragma unroll

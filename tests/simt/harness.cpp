@@ -46,7 +46,7 @@ int arena2_reserve(Ctx& c, size_t total, size_t keep)
 static Ctx& ctx()
 {
 	static Ctx c;
-	static int small[64];
+	static int small[256];
 	c.device = 0; c.h_small = small; c.sm_count = 2; c.launches = 0;
 	c.arena.reset(); c.arena.high = 0;
 	return c;

@@ -141,6 +141,7 @@ static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { for (int o = 
 
 void __syncthreads();
 int __syncthreads_or(int pred);
+static inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
