@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) k_src_rank(const u8* __restrict__ T, u32 
 					continue;
 				}
 				if (prev_sym < 0x100) {                           // the run that just ended: its byte was last seen one position back
+					__syncwarp();                                   // (every lane has read the tables for the previous position)
 					if (lane == 0) { last[prev_sym] = pos1 - 1; cur[prev_sym] = dst + 1; }
 					__syncwarp();
 				}
