@@ -656,31 +656,41 @@ __global__ void __launch_bounds__(256) k_inv_clear_text(uint4* __restrict__ text
 }
 
 // Replay of k_inv_walk_stream's loop: iteration i of warp w reads row i of w's stream.
+// What the kernel is short of is issue slots, not bandwidth (round 1: 125 warp instructions per 32-byte row, two or three
+// lanes leaving the common path in nearly every row), so everything per-row is kept to a few instructions:
+//   * records are decoded and range-checked when a ticket batch is staged in shared memory (all lanes, 4 records each),
+//     so a lane that starts a sub-chain reads back (end position, length) and nothing else;
+//   * the exit conditions (all tickets drawn, a failed check) can only change where tickets are drawn, and are voted on there;
+//   * the 16-byte window image is a 128-bit shift register: text positions fall by one per step, so the new byte enters
+//     at the bottom and a window that was filled from its top needs no alignment at all; a window left part-way is
+//     shifted into place once, on the way out;
+//   * a full window leaves as one 16-byte store, anything else as RED.OR.64 of its non-zero halves into the zeroed text
+//     (bytes a sub-chain does not own are zero in its image, so no byte ranges are worked out).
 __global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 S, const u64* __restrict__ rec,
                                                            StreamSpace sp, u8* __restrict__ out, int* __restrict__ err)
 {
 	__shared__ uint4 sdata[INV_WARPS][ST_CHUNK / 16];
-	__shared__ u64 srec[INV_WARPS][2][WALK_BATCH];
+	__shared__ uint2 srec[INV_WARPS][2][WALK_BATCH];             // decoded: .x end position, .y length (0 = nothing to place, bit 31 = failed a check)
 	if (*(volatile int*)err != 0) return;                       // the stream is incomplete: the host falls back
 	const u32 nodes = S + N_ANCHOR;
 	const u32 lane = lane_id(), w = threadIdx.x >> 5;
 	const u32 wgid = blockIdx.x * INV_WARPS + w;
 	const u32 cap = sp.cap0 + sp.cap1;
-	const u8* sbytes = reinterpret_cast<const u8*>(sdata[w]);
+	const u8* sbytes = reinterpret_cast<const u8*>(sdata[w]) + lane;
 	u32 next_t = 0, end_t = 0, base_t = 0, par = 0;
 	u32 prev_batch = ST_NONE, chunk = ST_NONE, row = ST_ROWS;
-	u32 id = REC_INVALID, left = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+	u32 left = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;                // left > 0: a sub-chain is being placed
 	i32 pos = 0, pos_end = 0;
-	bool done = false, bad = false;
+	bool done = false;
 	// (a replay that has diverged from the walk -- only possible after a failed check -- must not chase stale log
 	// entries: any failure ends the warp, and the iteration count is bounded by the rows that exist)
 	for (u32 iter = 0; iter < cap * ST_ROWS + 2; iter++) {
 		// ---- the ticket logic of take_ticket_log, batches read back from the log, records from shared memory
-		const bool need = !done && id == REC_INVALID;
+		const bool need = !done && left == 0;
 		const u32 nm = __ballot_sync(0xffffffffu, need);
 		if (nm != 0) {
 			const u32 cnt = __popc(nm), r = __popc(nm & lanemask_lt()), avail = end_t - next_t;
-			u32 my = REC_INVALID; u64 rv = 0;
+			u32 my = REC_INVALID; uint2 rv = make_uint2(0, 0);
 			if (need && r < avail) { my = next_t + r; rv = srec[w][par][my - base_t]; }
 			if (cnt > avail) {
 				u32 kb = 0;
@@ -693,22 +703,27 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 
 				#pragma unroll
 				for (int k = 0; k < (int)WALK_BATCH / 32; k++) {
 					const u32 q = base + k * 32 + lane;
-					srec[w][par][k * 32 + lane] = q < nodes ? rec[q] : pack3(0, PR_NXT_INVALID, 0);
+					uint2 dv = make_uint2(0, 0);
+					if (q < nodes) {
+						const u64 rr = rec[q];
+						const u32 nxt = pr_nxt(rr), L = pr_len(rr);
+						if (nxt != PR_NXT_INVALID) {
+							const i64 pe = (i64)(nxt - S) * step + pr_dist(rr);
+							const bool ok = nxt >= S && nxt < nodes && L != 0 && pe <= n && pe >= (i64)L;
+							dv = ok ? make_uint2((u32)pe, L) : make_uint2(0, 0x80000000u);
+						}
+					}
+					srec[w][par][k * 32 + lane] = dv;
 				}
 				__syncwarp();
 				if (need && r >= avail) { my = base + (r - avail); rv = srec[w][par][my - base]; }
 				next_t = base + (cnt - avail); end_t = base + WALK_BATCH; base_t = base;
 			} else next_t += cnt;
-			if (need && my >= nodes) { done = true; my = REC_INVALID; }
-			if (my != REC_INVALID && pr_nxt(rv) != PR_NXT_INVALID) {
-				const u32 nxt = pr_nxt(rv), L = pr_len(rv);
-				const i64 pe = (i64)(nxt - S) * step + pr_dist(rv);
-				if (nxt < S || nxt >= nodes || L == 0 || pe > n || pe < (i64)L) { dev_fail(err, DE_CHAIN_RANGE); bad = true; }
-				else { id = my; left = L; pos = pos_end = (i32)pe; a0 = a1 = a2 = a3 = 0; }
-			}
+			if (need && my >= nodes) { done = true; rv.y = 0; }
+			if (rv.y & 0x80000000u) { dev_fail(err, DE_CHAIN_RANGE); done = true; }      // (the call fails; this lane stops, the others stay inside their checked ranges)
+			else if (rv.y != 0) { left = rv.y; pos = pos_end = (i32)rv.x; a0 = a1 = a2 = a3 = 0; }
+			if (__ballot_sync(0xffffffffu, !done) == 0) break;       // (the only place it can change)
 		}
-		if (__any_sync(0xffffffffu, bad)) break;
-		if (__ballot_sync(0xffffffffu, !done) == 0) break;
 		if (row == ST_ROWS) {
 			u32 c = 0;
 			if (lane == 0) c = (chunk == ST_NONE) ? sp.chunk_head[wgid] : sp.chunk_next[chunk];
@@ -721,18 +736,29 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_place(i32 n, i32 step, u32 
 			__syncwarp();
 			chunk = c; row = 0;
 		}
-		if (id != REC_INVALID) {
-			const u32 c = sbytes[row * 32 + lane];
+		if (left != 0) {
+			const u32 c = sbytes[row * 32];
 			pos--; left--;
-			const bool stop = left == 0;
-			const u32 k = ((u32)pos >> 2) & 3u, bits = c << (((u32)pos & 3u) * 8);
-			a0 |= (k == 0) ? bits : 0u; a1 |= (k == 1) ? bits : 0u; a2 |= (k == 2) ? bits : 0u; a3 |= (k == 3) ? bits : 0u;
-			if (((u32)pos & 15u) == 0 || stop) {
-				const i32 wbase = pos & ~15;
-				flush_window(out + wbase, (u32)(pos - wbase), (u32)min(16, pos_end - wbase), a0, a1, a2, a3);
+			a3 = (a3 << 8) | (a2 >> 24); a2 = (a2 << 8) | (a1 >> 24); a1 = (a1 << 8) | (a0 >> 24); a0 = (a0 << 8) | c;
+			const u32 sh = (u32)pos & 15u;
+			if (sh == 0 || left == 0) {
+				u8* win = out + (pos & ~15);
+				if (sh == 0 && pos_end - pos >= 16) *reinterpret_cast<uint4*>(win) = make_uint4(a0, a1, a2, a3);   // the whole window is this sub-chain's
+				else {
+					// left part-way (or entered part-way): the newest byte belongs at offset sh -- whole words by selects, the
+					// rest by funnel shifts, no branches (the lanes that get here differ in sh)
+					const u32 q = sh >> 2, rb = (sh & 3u) * 8;
+					const u32 w0 = q == 0 ? a0 : 0u;
+					const u32 w1 = q == 0 ? a1 : q == 1 ? a0 : 0u;
+					const u32 w2 = q == 0 ? a2 : q == 1 ? a1 : q == 2 ? a0 : 0u;
+					const u32 w3 = q == 0 ? a3 : q == 1 ? a2 : q == 2 ? a1 : a0;
+					const u64 lo = ((u64)__funnelshift_l(w0, w1, rb) << 32) | (u64)(w0 << rb);
+					const u64 hi = ((u64)__funnelshift_l(w2, w3, rb) << 32) | (u64)__funnelshift_l(w1, w2, rb);
+					if (lo) atomicOr(reinterpret_cast<unsigned long long*>(win), (unsigned long long)lo);       // result unused: RED.OR.64
+					if (hi) atomicOr(reinterpret_cast<unsigned long long*>(win) + 1, (unsigned long long)hi);
+				}
 				a0 = a1 = a2 = a3 = 0;
 			}
-			if (stop) id = REC_INVALID;
 		}
 		row++;
 	}
