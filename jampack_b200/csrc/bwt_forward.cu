@@ -37,6 +37,9 @@ struct FwdMeta {
 	u32 code[256];
 	i32 sigma, bits, depth, key_bits;   // bits: per symbol (reported); depth: symbols per key; key_bits: bit length of the largest key
 	u32 eq4;                            // aligned 16-byte vectors of one repeated byte: a cheap screen for long single-symbol runs
+	u32 min_depth;                      // context-coded keys: the fewest symbols any key covers
+	u32 ck_pad;
+	unsigned long long ck_bits, ck_syms; // ... and the sampled positions with the total length of their codewords
 	u32 hist[256];
 };
 
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(256) k_fwd_codes(FwdMeta* __restrict__ meta)
 		meta->bits = bit_length((u64)total);
 		meta->depth = depth;
 		meta->key_bits = bit_length(span - 1);
+		meta->min_depth = 0x7fffffffu;
 	}
 }
 
@@ -176,6 +180,232 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 	#pragma unroll
 	for (int k = 0; k < 8; k++) sum += h[k][t];
 	tile_hist[(size_t)t * stride + blockIdx.x] = sum;
+}
+
+
+// ---- 2a. context-coded keys --------------------------------------------------------------------------------
+// The mixed-radix key above spends log2(sigma+1) bits on every symbol whatever the text looks like: 8 symbols of source
+// text, 10 of the order-2 Markov benchmark -- and it is the number of SYMBOLS in the key that decides how much of the
+// block the doubling rounds still have to touch. Here the key is a bit string instead: the first `order` symbols as
+// fixed-width fields, then the symbols that follow, each as a codeword of an ALPHABETIC (order-preserving, prefix-free)
+// code chosen by the `order` symbols before it:
+//     key(u) = sym(u) [sym(u+1)] . cw(u+order) cw(u+order+1) ...   cut after key_bits bits,
+//     cw(i)  = code of T[i] in the context T[i-order .. i-1]  (a property of the position, not of the key it lands in).
+// Two suffixes use the same code table up to their first difference, so the numeric order of two different keys is the
+// lexicographic order of the suffixes -- however many symbols either key happens to cover. Equal keys share at least
+// `order` + (complete codewords inside the cut) symbols; the minimum of that count over the block is the h the doubling
+// starts from. Groups come out FINER than "equal h-prefix" (a key usually covers far more than the minimum), which the
+// rounds do not mind: a group only ever has to consist of suffixes that agree on h symbols and to sit where the true
+// order puts it. The code tables come from one pass over the text: which (context, symbol) pairs occur at all (exact, a
+// bitmap) and how often (counted on a sample); a pair that does not occur gets no codeword, so the frequent successors
+// of a context keep codewords of about -log2 p bits. With a key bit worth about a bit of information, 6 radix passes
+// cover what 8 did (key_bits = 48) and the first doubling round finds a few per cent of the block still unsorted
+// instead of half of it.
+constexpr int CK_LMAX = 12;                       // longest codeword (length-limited so that a key covers >= order + 4 symbols)
+constexpr int CK_LA = 72;                         // symbols read beyond the tile: a codeword has >= 1 bit, a key < 64
+constexpr u32 CK_MAX_S2 = 80;                     // order 2 up to 79 symbols + end: 80^3 table entries
+struct CtxTabs { u32* present; u32* counts; u16* table; u32 S, order, entries; };
+
+__device__ __forceinline__ u32 ck_index(u32 order, u32 S, u32 c2, u32 c1, u32 c0) { return ((order == 2 ? c2 * S + c1 : c1) * S) + c0; }
+
+// pass over the text: exact presence bitmap (privatised in shared memory, test before set) + sampled counts.
+// A thread takes 16 consecutive positions (one 16-byte load); a block 4096 at a time, every `every`-th of them counted.
+__global__ void __launch_bounds__(256) k_ctx_scan(const u8* __restrict__ T, u32 n, const FwdMeta* __restrict__ meta, CtxTabs ct, u32 every)
+{
+	extern __shared__ __align__(16) u8 ck_smem[];
+	u32* sb = reinterpret_cast<u32*>(ck_smem);
+	__shared__ u16 code[256];
+	const u32 t = threadIdx.x, words = (ct.entries + 31) / 32;
+	const u32 order = ct.order, S = ct.S;
+	code[t] = (u16)meta->code[t];
+	for (u32 i = t; i < words; i += 256) sb[i] = 0;
+	__syncthreads();
+	const u32 chunks = (n + 4095) / 4096;
+	for (u32 q = blockIdx.x; q < chunks; q += gridDim.x) {
+		const u32 p0 = (q * 256 + t) * 16;
+		const bool sampled = q % every == 0;             // (uniform over the block)
+		u32 wd[4] = {0, 0, 0, 0};
+		if (p0 + 16 <= n) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(T + p0)); wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w; }
+		else for (u32 k = 0; k < 16 && p0 + k < n; k++) wd[k >> 2] |= (u32)T[p0 + k] << ((k & 3) * 8);
+		u32 c2 = (p0 >= 2 && p0 - 2 < n) ? code[T[p0 - 2]] : 0u, c1 = (p0 >= 1 && p0 - 1 < n) ? code[T[p0 - 1]] : 0u;
+		#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const u32 j = p0 + k;
+			const u32 c0 = code[(wd[k >> 2] >> ((k & 3) * 8)) & 255u];
+			const bool ok = j >= order && j < n;
+			const u32 idx = ok ? ck_index(order, S, c2, c1, c0) : 0xffffffffu;
+			if (ok) {
+				const u32 bit = 1u << (idx & 31);
+				if (!(sb[idx >> 5] & bit)) atomicOr(&sb[idx >> 5], bit);
+			}
+			if (sampled) {
+				const u32 peers = __match_any_sync(0xffffffffu, idx);
+				if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&ct.counts[idx], (u32)__popc(peers));
+			}
+			c2 = c1; c1 = c0;
+		}
+	}
+	if (blockIdx.x == 0 && t == 0) {                 // the end of the text, in its context
+		const u32 idx = ck_index(order, S, order == 2 ? code[T[n - 2]] : 0u, code[T[n - 1]], 0u);
+		atomicOr(&sb[idx >> 5], 1u << (idx & 31));
+	}
+	__syncthreads();
+	for (u32 i = t; i < words; i += 256) { const u32 v = sb[i]; if (v) atomicOr(&ct.present[i], v); }
+}
+
+// block = one context: a weight-balanced alphabetic tree over the symbols that occur in it (every thread walks down to
+// its own leaf; all threads of a node compute the same split), at most CK_LMAX levels deep
+__global__ void __launch_bounds__(288) k_ctx_codes(CtxTabs ct, FwdMeta* __restrict__ meta)
+{
+	__shared__ u32 W[288];                            // inclusive weight sums over the leaves of this context
+	__shared__ u32 ws[32];
+	const u32 t = threadIdx.x, ctx = blockIdx.x;
+	const u32 idx = ctx * ct.S + t;
+	const bool here = t < ct.S && ((ct.present[idx >> 5] >> (idx & 31)) & 1u);
+	u32 K, wtot;
+	const u32 k = block_incl_sum(here ? 1u : 0u, ws, &K) - (here ? 1u : 0u);
+	const u32 cnt = here ? min(ct.counts[idx], 1u << 23) : 0u;                    // (the sample is <= 2^23 positions: the sums fit 32 bits)
+	const u32 wgt = here ? 16u * cnt + 1u : 0u;
+	const u32 inc = block_incl_sum(wgt, ws, &wtot);
+	if (K == 0) return;
+	if (here) W[k] = inc;
+	__syncthreads();
+	u32 lo = 0, hi = here ? K - 1 : 0u, len = 0, cw = 0;
+	while (lo < hi) {
+		const u32 base = lo ? W[lo - 1] : 0u, tot = W[hi] - base;
+		const u32 target = base + (tot + 1) / 2;
+		u32 a = lo, b = hi - 1;                       // smallest m in [lo, hi-1] with W[m] >= target, else hi-1
+		while (a < b) { const u32 mid = (a + b) >> 1; if (W[mid] >= target) b = mid; else a = mid + 1; }
+		u32 m = a;
+		if (m > lo) {                                 // the neighbour on the left may balance better
+			const u64 l1 = (u64)(W[m] - base), l0 = (u64)(W[m - 1] - base);
+			const u64 d1 = 2 * l1 > tot ? 2 * l1 - tot : tot - 2 * l1, d0 = 2 * l0 > tot ? 2 * l0 - tot : tot - 2 * l0;
+			if (d0 < d1) m--;
+		}
+		const u32 cap = 1u << (CK_LMAX - len - 1);    // leaves either side may still hold
+		if (m + 1 - lo > cap) m = lo + cap - 1;
+		if (hi - m > cap) m = hi - cap;
+		if (k <= m) { hi = m; cw <<= 1; } else { lo = m + 1; cw = (cw << 1) | 1u; }
+		len++;
+	}
+	if (K == 1) { len = 1; cw = 0; }                  // (a codeword has at least one bit: a key never covers more than it has bits)
+	if (here) ct.table[idx] = (u16)((len << 12) | cw);
+	// what the code spends on the sample: the host sizes the keys by it
+	u32 bits_total, cnt_total;
+	block_incl_sum(cnt * len, ws, &bits_total);
+	block_incl_sum(cnt, ws, &cnt_total);
+	if (t == 0 && cnt_total) { atomicAdd(&meta->ck_bits, (unsigned long long)bits_total); atomicAdd(&meta->ck_syms, (unsigned long long)cnt_total); }
+}
+
+// keys of one radix tile + the histogram of their lowest digit + the smallest number of symbols a key covers
+__global__ void __launch_bounds__(256) k_fwd_keys_ctx(const u8* __restrict__ T, i32 n, FwdMeta* __restrict__ meta, CtxTabs ct,
+                                                      u32 sym_bits, u32 key_bits, u64* __restrict__ keys, u32* __restrict__ vals,
+                                                      u32* __restrict__ tile_hist, u32 stride, int* __restrict__ err)
+{
+	constexpr int SPAN = KEY_TILE + CK_LA;
+	constexpr int PER = (SPAN + 255) / 256;
+	__shared__ u16 sc[SPAN];
+	__shared__ u16 P[SPAN + 1];                       // bit offset of each position's codeword; P[SPAN] = end of the last one
+	__shared__ u32 buf[SPAN * CK_LMAX / 32 + 4];      // the codewords back to back, most significant bit first
+	__shared__ u16 code[256];
+	__shared__ u32 h[8][256];
+	__shared__ u32 ws[32];
+	__shared__ u32 s_min;
+	const int t = threadIdx.x, w = t >> 5;
+	code[t] = (u16)meta->code[t];
+	for (int i = t; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+	for (int i = t; i < SPAN * CK_LMAX / 32 + 4; i += 256) buf[i] = 0;
+	if (t == 0) s_min = 0xffffffffu;
+	__syncthreads();
+	const i64 base = (i64)blockIdx.x * KEY_TILE;
+	for (int i = t; i < SPAN; i += 256) { const i64 p = base + i; sc[i] = p < n ? code[T[p]] : (u16)0; }
+	__syncthreads();
+	const u32 order = ct.order, S = ct.S;
+	// codeword of every position of the span (thread t: PER consecutive positions), their bit offsets
+	u32 e[PER]; u32 mine = 0;
+	#pragma unroll
+	for (int k = 0; k < PER; k++) {
+		const int i = t * PER + k;
+		e[k] = 0;
+		if (i < SPAN && i >= (int)order && base + i <= n) {
+			e[k] = ct.table[ck_index(order, S, order == 2 ? sc[i - 2] : 0u, sc[i - 1], sc[i])];
+			if ((e[k] >> 12) == 0) dev_fail(err, DE_FWD_ROUNDS);          // a pair the scan did not see: cannot happen
+		}
+		mine += e[k] >> 12;
+	}
+	u32 total;
+	u32 off = block_incl_sum(mine, ws, &total) - mine;
+	{
+		// the thread's codewords are consecutive bits of the stream: assembled in a register, left-aligned from the
+		// word boundary below `off`; whole words are stored, the ragged first and last ones OR-ed in
+		u32 wi = off >> 5, fill = off & 31u;
+		bool shared_word = fill != 0;
+		u64 acc = 0;
+		#pragma unroll
+		for (int k = 0; k < PER; k++) {
+			const int i = t * PER + k;
+			if (i < SPAN) {
+				P[i] = (u16)off;
+				const u32 len = e[k] >> 12;
+				if (len) acc |= (u64)(e[k] & 0xfffu) << (64 - fill - len);  // (fill < 32, len <= 12)
+				fill += len; off += len;
+				if (fill >= 32) {
+					if (shared_word) atomicOr(&buf[wi], (u32)(acc >> 32)); else buf[wi] = (u32)(acc >> 32);
+					shared_word = false;
+					acc <<= 32; fill -= 32; wi++;
+				}
+			}
+		}
+		if (fill && (u32)(acc >> 32)) atomicOr(&buf[wi], (u32)(acc >> 32));
+	}
+	if (t == 255) P[SPAN] = (u16)total;
+	__syncthreads();
+	const u32 B = key_bits - order * sym_bits;        // bits of the coded part
+	#pragma unroll 4
+	for (int j = 0; j < KEY_TILE / 256; j++) {
+		const int li = j * 256 + t;
+		const i64 p = base + li;
+		if (p < n) {
+			const u32 o = P[li + order], wi = o >> 5, sh = o & 31u;
+			const u32 w0 = buf[wi], w1 = buf[wi + 1], w2 = buf[wi + 2];
+			const u64 win = ((u64)__funnelshift_l(w1, w0, sh) << 32) | (u64)__funnelshift_l(w2, w1, sh);
+			const u64 fixed = order == 2 ? ((u64)sc[li] << sym_bits) | sc[li + 1] : (u64)sc[li];
+			const u64 k = (fixed << B) | (win >> (64 - B));
+			keys[p] = k;
+			vals[p] = (u32)p;
+			atomicAdd(&h[w][(u32)k & 255u], 1u);
+		}
+	}
+	// symbols covered: order + complete codewords inside the cut, i.e. the largest c <= 64 with P[i+order+c] - P[i+order] <= B.
+	// The end of the window never moves back from one position to the next: a thread walks 16 consecutive positions.
+	u32 dmin = 0xffffffffu;
+	{
+		const int l0 = t * (KEY_TILE / 256);
+		u32 end = 0;
+		for (int k = 0; k < KEY_TILE / 256; k++) {
+			const int li = l0 + k;
+			if (base + li >= n) break;
+			const u32 i0 = (u32)li + order, o = P[i0];
+			if (k == 0) {
+				u32 a = 0, b = 64;
+				while (a < b) { const u32 mid = (a + b + 1) >> 1; if ((u32)P[i0 + mid] - o <= B) a = mid; else b = mid - 1; }
+				end = i0 + a;
+			} else {
+				if (end < i0) end = i0;
+				while (end < i0 + 64 && (u32)P[end + 1] - o <= B) end++;
+			}
+			dmin = min(dmin, order + (end - i0));
+		}
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+	if ((t & 31) == 0) atomicMin(&s_min, dmin);
+	__syncthreads();
+	u32 sum = 0;
+	#pragma unroll
+	for (int k = 0; k < 8; k++) sum += h[k][t];
+	tile_hist[(size_t)t * stride + blockIdx.x] = sum;
+	if (t == 0 && s_min != 0xffffffffu) atomicMin(&meta->min_depth, s_min);
 }
 
 
@@ -1561,19 +1791,61 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		R = (u32)c.h_small[14]; M = (u32)c.h_small[15];
 		if (R == 0 || R > rt.cap) bypass = false;          // nothing to place, or more runs than the tables hold: plain doubling
 	}
+	// Context-coded keys for ordinary blocks (the run bypass and the representatives of a periodic block reason about a fixed
+	// number of symbols per key and keep the mixed-radix form). JP_BWT_FWD_CTXKEYS=0/1 overrides the size threshold,
+	// JP_BWT_FWD_KEYPASSES the number of radix passes.
+	const u32 ck_S = (u32)c.h_small[16] + 1;
+	const u32 ck_order = ck_S <= CK_MAX_S2 ? 2u : 1u;
+	const u32 ck_entries = ck_order == 2 ? ck_S * ck_S * ck_S : ck_S * ck_S;
+	bool ctx_keys = !premode && !bypass && n >= (1 << 20);
+	if (const char* e = getenv("JP_BWT_FWD_CTXKEYS")) ctx_keys = !premode && !bypass && atoi(e) != 0 && n >= 4096;
+	if (ctx_keys && Arena::align(((size_t)ck_entries + 31) / 32 * 4) + Arena::align((size_t)ck_entries * 4) + (size_t)ck_entries * 2 > 2 * b.usz) ctx_keys = false;
+	int ck_key_bits = 8 * std::min(8, std::max(4, (bit_length((u64)n) + 13 + 7) / 8));
+	if (const char* e = getenv("JP_BWT_FWD_KEYPASSES")) ck_key_bits = 8 * std::min(8, std::max(3, atoi(e)));
+	if (ck_key_bits > 63) ck_key_bits = 63;
+	if (ck_key_bits < (int)(ck_order * (u32)bits) + 16) ctx_keys = false;
 	if (!premode) {
 		const u32 n_sorted = bypass ? (u32)n - M : (u32)n;
 		if (bypass) {
 			st->bypass_suffixes = (i32)M; st->bypass_runs = (i32)R;
 			k_run_tile_scan<<<1, 1024, 0, s>>>(rt.tile_base, ktiles, (u32)n); JP_LAUNCH(c);
 			k_fwd_keys<true><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], nullptr, 0, rt.bits, rt.tile_base); JP_LAUNCH(c);
+		} else if (ctx_keys) {
+			// context-coded keys: the tables live in the second key buffer until the first radix pass overwrites it
+			CtxTabs ct; ct.S = ck_S; ct.order = ck_order; ct.entries = ck_entries;
+			const size_t words = ((size_t)ck_entries + 31) / 32;
+			ct.present = reinterpret_cast<u32*>(b.unit[2]);
+			ct.counts = ct.present + Arena::align(words * 4) / 4;
+			ct.table = reinterpret_cast<u16*>(ct.counts + Arena::align((size_t)ck_entries * 4) / 4);
+			JP_CUDA(cudaMemsetAsync(ct.present, 0, Arena::align(words * 4) + Arena::align((size_t)ck_entries * 4), s));
+			const u32 every = std::max(1u, (u32)n >> 22);                    // counts from ~4 M sampled positions
+			const u32 chunks = ((u32)n + 4095) / 4096;
+			const u32 per_sm = (u32)std::max<size_t>(1, std::min<size_t>(6, (200u << 10) / (words * 4 + 1024)));
+			if (cudaFuncSetAttribute(k_ctx_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)) != cudaSuccess) { set_error_detail("k_ctx_scan smem attribute"); return JP_ERR_CUDA; }
+			k_ctx_scan<<<std::min(chunks, (u32)c.sm_count * per_sm), 256, words * 4, s>>>(d_T, (u32)n, b.meta, ct, every); JP_LAUNCH(c);
+			k_ctx_codes<<<ck_order == 2 ? ck_S * ck_S : ck_S, 288, 0, s>>>(ct, b.meta); JP_LAUNCH(c);
+			if (!getenv("JP_BWT_FWD_KEYPASSES")) {
+				// Key length. With a code that fits, a key bit is worth about a bit: log2 n + 13 of them leave a few per cent of
+				// the block to the rounds (measured: 5 passes beat 6 and 8 on the order-2 Markov and the uniform 64 MiB blocks).
+				// An order-1 code that compresses well says the text has structure, and then it has more than one symbol of
+				// context can see (source text: 3.8 of 7.7 bits): all 63 bits pay there.
+				unsigned long long* h_ck = reinterpret_cast<unsigned long long*>(c.h_small + 24);
+				JP_CUDA(cudaMemcpyAsync(h_ck, &b.meta->ck_bits, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+				JP_CUDA(cudaStreamSynchronize(s));
+				const double rate = h_ck[1] ? (double)h_ck[0] / (double)h_ck[1] : (double)bits;
+				if (ck_order == 1 && rate < 0.75 * (double)bits) ck_key_bits = 63;
+				st->symbol_bits = (i32)(rate + 0.5);
+			}
+			k_fwd_keys_ctx<<<ktiles, 256, 0, s>>>(d_T, n, b.meta, ct, (u32)bits, (u32)ck_key_bits, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
+			                                     rs_stride((u32)radix_tiles((size_t)n)), b.err); JP_LAUNCH(c);
+			JP_CUDA(cudaMemcpyAsync(c.h_small + 22, &b.meta->min_depth, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
 		} else {
 			k_fwd_keys<false><<<ktiles, 256, 0, s>>>(d_T, n, b.meta, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
 			                                         rs_stride((u32)radix_tiles((size_t)n)), nullptr, nullptr); JP_LAUNCH(c);
 		}
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[1], s));
-		const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
+		const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, ctx_keys ? ck_key_bits : key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
 		if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[2], s));
@@ -1608,6 +1880,16 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	JP_CUDA(cudaEventRecord(c.ev[3], s));
 	act = 0;
 	A = (u32)c.h_small[8]; G = (u32)c.h_small[9];
+	i64 depth0 = depth;                                                 // symbols every initial key is known to cover
+	if (ctx_keys) {
+		depth0 = (i64)(u32)c.h_small[22];
+		if (depth0 < (i64)ck_order || depth0 > (i64)n + 64) { set_error_detail("context-coded keys cover %lld symbols", (long long)depth0); return JP_ERR_INTERNAL; }
+		if (depth0 > 64) depth0 = 64;
+		if (depth0 < 1) depth0 = 1;
+		h = depth0;
+		st->initial_depth = (i32)depth0;
+		if (trace_rounds) fprintf(stderr, "[jp_bwt keys] context-coded: order %u, %u symbols, %d key bits, every key covers >= %lld symbols; active after the sort %u\n", ck_order, ck_S - 1, ck_key_bits, (long long)depth0, A);
+	}
 
 	// Periodic repeats: when most of the block is still unsorted, look for a dominant distance between group neighbours.
 	const u32 shared_levels = bypass ? (u32)c.h_small[21] : 0;
@@ -1628,7 +1910,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 			JP_CUDA(cudaMemcpyAsync(c.h_small + 14, ct + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 			JP_CUDA(cudaStreamSynchronize(s));
 			const u32 p = (u32)c.h_small[14], hits = (u32)c.h_small[15];
-			h_a = depth;
+			h_a = depth0;
 			while (h_a < (i64)p) h_a *= 2;
 			if (p >= 1 && (u64)hits * PER_SAMPLE * 2 >= (u64)A && h_a * 4 <= (i64)n) {
 				periodic = true;

@@ -538,6 +538,53 @@ def test_single_walk_rejects_corrupt_input(jp, orc, single_walk_env):
     assert (jp.inverse(B) == T).all() and jp.last_stats().stream_chunks > 0
 
 
+def _word_text(n, seed):
+    rng = np.random.default_rng(seed)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 10)), dtype=np.uint8)) for _ in range(2000)]
+    pick = rng.zipf(1.2, n // 3) % len(words)
+    return np.frombuffer(b" ".join(words[i] for i in pick), dtype=np.uint8)[:n].copy()
+
+
+@pytest.mark.parametrize("kind,n,seed", [("markov2", 2 * MiB + 77, 1), ("uniform", MiB, 2), ("words", 3 * MiB, 3), ("dna", 2 * MiB + 1, 4),
+                                         ("words+bytes", 4 * MiB, 5), ("markov2", 32 * MiB, 6), ("small", 5000, 7)])
+@pytest.mark.parametrize("passes", [None, "4", "6", "8"])
+def test_forward_context_coded_keys_are_bit_exact(jp, orc, kind, n, seed, passes):
+    """Initial keys as bit strings of context-chosen alphabetic codewords (bwt_forward.cu 2a): forced on, with the
+    key length the host picks and with 32-, 48- and 63-bit keys, against the compiled reference; the mixed-radix keys
+    (switch off) must give the same block."""
+    rng = np.random.default_rng(seed)
+    if kind == "words":
+        T = _word_text(n, seed)
+    elif kind == "dna":
+        T = (rng.integers(0, 4, n) + 65).astype(np.uint8)
+    elif kind == "words+bytes":
+        T = _word_text(n, seed); T[n // 3: n // 3 + 200000] = rng.integers(0, 256, 200000).astype(np.uint8)
+    elif kind == "small":
+        T = (rng.integers(0, 7, n) + 48).astype(np.uint8)
+    else:
+        T = orc.gen(kind, n, seed)
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    keys = ("JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_KEYPASSES")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        os.environ["JP_BWT_FWD_CTXKEYS"] = "1"
+        if passes is not None:
+            os.environ["JP_BWT_FWD_KEYPASSES"] = passes
+        got = jp.forward(T, prefill=0x5C)
+        st = jp.last_stats()
+        os.environ["JP_BWT_FWD_CTXKEYS"] = "0"
+        plain = jp.forward(T, prefill=0x5C)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert (got == want).all() and (plain == want).all()
+    if kind == "markov2" and n >= 32 * MiB and passes in (None, "6", "8"):
+        assert st.active_fraction[0] < 0.1, st.active_fraction[:3]      # the coded keys leave the rounds a few per cent of the block
+
+
 @pytest.mark.parametrize("kind,n,seed", [("alla", MiB, 0), ("alla", 360, 0), ("repetitive", MiB, 3), ("markov2", MiB + 77, 1),
                                          ("zero_pages", 3 * MiB, 5), ("runs", 2 * MiB, 6), ("tar_like", 4 * MiB, 7), ("alla", 40 * MiB, 0)])
 @pytest.mark.parametrize("force", [None, "1"])

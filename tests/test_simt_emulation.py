@@ -155,6 +155,52 @@ def test_emulated_forward_with_run_bypass(emu, orc, name):
         assert rounds1 < rounds0, (rounds0, rounds1)
 
 
+def _coded_key_blocks():
+    """Blocks for the context-coded initial keys: both model orders, a compressible order-1 text (63-bit keys), the end of the
+    block inside the last keys, a length that is not a multiple of the key tile."""
+    rng = np.random.default_rng(31)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(300)]
+    zipf = rng.zipf(1.3, 40000) % len(words)
+    text = np.frombuffer(b" ".join(words[i] for i in zipf), dtype=np.uint8)
+    wide = np.concatenate([text[:60000], rng.integers(0, 256, 4000, dtype=np.uint8), text[:30000]])   # > 79 symbols: order 1
+    return {
+        "order2-dna": rng.integers(0, 4, 40007, dtype=np.uint8) + 65,
+        "order2-words": text[:90000 + 13],
+        "order1-words-and-bytes": wide,
+        "order1-uniform": rng.integers(0, 256, 61000, dtype=np.uint8),
+        "short": rng.integers(0, 3, 4200, dtype=np.uint8) + 48,
+        "tail-of-equal-symbols": np.concatenate([rng.integers(0, 5, 30000, dtype=np.uint8) + 65, np.full(25, 65, np.uint8)]),
+    }
+
+
+@pytest.mark.parametrize("name", list(_coded_key_blocks()))
+@pytest.mark.parametrize("passes", ["", "4", "8"])
+def test_emulated_forward_with_context_coded_keys(emu, orc, name, passes):
+    """the initial keys are bit strings of context-chosen alphabetic codewords; the doubling starts from the
+    fewest symbols any key covers. Forced on (the default engages it from 1 MiB), with the key length the host picks
+    and with the shortest and longest keys."""
+    T = np.ascontiguousarray(_coded_key_blocks()[name])
+    want = orc.forward(T, "port", prefill=0x5C)
+    keys = ("JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_KEYPASSES", "JP_BWT_FWD_BYPASS")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        os.environ["JP_BWT_FWD_CTXKEYS"] = "1"
+        os.environ["JP_BWT_FWD_BYPASS"] = "0"
+        if passes:
+            os.environ["JP_BWT_FWD_KEYPASSES"] = passes
+        else:
+            os.environ.pop("JP_BWT_FWD_KEYPASSES", None)
+        rc, got, rounds, launches = emu.forward(T)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert rc == 0
+    assert np.array_equal(got, want), f"{name}: first difference at {int(np.argmax(got != want))}"
+
+
 def _periodic(n, p, sig, defects, seed):
     r = np.random.default_rng(seed)
     T = np.tile(r.integers(0, sig, p).astype(np.uint8), n // p + 1)[:n].copy()
