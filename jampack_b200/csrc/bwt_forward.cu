@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(288) k_ctx_codes(CtxTabs ct, FwdMeta* __restri
 
 // keys of one radix tile + the histogram of their lowest digit + the smallest number of symbols a key covers
 __global__ void __launch_bounds__(256) k_fwd_keys_ctx(const u8* __restrict__ T, i32 n, FwdMeta* __restrict__ meta, CtxTabs ct,
-                                                      u32 sym_bits, u32 key_bits, u64* __restrict__ keys, u32* __restrict__ vals,
+                                                      u32 sym_bits, u32 key_bits, u32 idx_bits, u64* __restrict__ keys, u32* __restrict__ vals,
                                                       u32* __restrict__ tile_hist, u32 stride, int* __restrict__ err)
 {
 	constexpr int SPAN = KEY_TILE + CK_LA;
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(256) k_fwd_keys_ctx(const u8* __restrict__ T, 
 			const u64 win = ((u64)__funnelshift_l(w1, w0, sh) << 32) | (u64)__funnelshift_l(w2, w1, sh);
 			const u64 fixed = order == 2 ? ((u64)sc[li] << sym_bits) | sc[li + 1] : (u64)sc[li];
 			const u64 k = (fixed << B) | (win >> (64 - B));
-			keys[p] = k;
-			vals[p] = (u32)p;
+			if (idx_bits) keys[p] = (k << idx_bits) | (u64)p;             // packed records: the position rides below the key
+			else { keys[p] = k; vals[p] = (u32)p; }
 			atomicAdd(&h[w][(u32)k & 255u], 1u);
 		}
 	}
@@ -713,6 +713,23 @@ __global__ void __launch_bounds__(256) k_fwd_flags(const KT* __restrict__ K, u32
 	}
 	if (j0 + 4 <= n) *reinterpret_cast<u32*>(F + j0) = w;
 	else for (int b = 0; b < 4 && j0 + b < n; b++) F[j0 + b] = (u8)(w >> (8 * b));
+}
+
+// packed records (key << idx_bits | position) in sorted order -> the suffix array and the head flags
+__global__ void __launch_bounds__(256) k_fwd_unpack(const u64* __restrict__ K, u32 n, u32 idx_bits, u32* __restrict__ SA, u8* __restrict__ F)
+{
+	const u32 j0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+	if (j0 >= n) return;
+	const u64 mask = ((u64)1 << idx_bits) - 1;
+	u64 prev = j0 ? K[j0 - 1] >> idx_bits : ~(K[0] >> idx_bits);
+	u32 w = 0, v[4] = {0, 0, 0, 0};
+	#pragma unroll
+	for (int b = 0; b < 4; b++) {
+		const u32 j = j0 + b;
+		if (j < n) { const u64 r = K[j], k = r >> idx_bits; v[b] = (u32)(r & mask); w |= (k != prev ? 1u : 0u) << (8 * b); prev = k; }
+	}
+	if (j0 + 4 <= n) { *reinterpret_cast<u32*>(F + j0) = w; *reinterpret_cast<uint4*>(SA + j0) = make_uint4(v[0], v[1], v[2], v[3]); }
+	else for (int b = 0; b < 4 && j0 + b < n; b++) { F[j0 + b] = (u8)(w >> (8 * b)); SA[j0 + b] = v[b]; }
 }
 
 __global__ void __launch_bounds__(GS_THREADS) k_grp_reduce(const u8* __restrict__ F, const u32* __restrict__ AP, u32 A, GAgg* __restrict__ agg)
@@ -1804,6 +1821,11 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	if (const char* e = getenv("JP_BWT_FWD_KEYPASSES")) ck_key_bits = 8 * std::min(8, std::max(3, atoi(e)));
 	if (ck_key_bits > 63) ck_key_bits = 63;
 	if (ck_key_bits < (int)(ck_order * (u32)bits) + 16) ctx_keys = false;
+	// Packed records: when short keys will do and the positions leave room for them in a 64-bit word (blocks up to 64 MiB),
+	// key and position travel as one word and the sort moves 16 bytes per pass and suffix instead of 24.
+	const int ck_idx_bits = bit_length((u64)n - 1);
+	bool ck_packed = ctx_keys && ck_key_bits <= 40 && 64 - ck_idx_bits >= ck_key_bits - 2 && !getenv("JP_BWT_FWD_KEYPASSES");
+	if (const char* e = getenv("JP_BWT_FWD_PACKED")) ck_packed = ctx_keys && atoi(e) != 0 && 64 - ck_idx_bits >= (int)(ck_order * (u32)bits) + 16;
 	if (!premode) {
 		const u32 n_sorted = bypass ? (u32)n - M : (u32)n;
 		if (bypass) {
@@ -1833,10 +1855,11 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 				JP_CUDA(cudaMemcpyAsync(h_ck, &b.meta->ck_bits, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 				JP_CUDA(cudaStreamSynchronize(s));
 				const double rate = h_ck[1] ? (double)h_ck[0] / (double)h_ck[1] : (double)bits;
-				if (ck_order == 1 && rate < 0.75 * (double)bits) ck_key_bits = 63;
+				if (ck_order == 1 && rate < 0.75 * (double)bits) { ck_key_bits = 63; if (!getenv("JP_BWT_FWD_PACKED")) ck_packed = false; }
 				st->symbol_bits = (i32)(rate + 0.5);
 			}
-			k_fwd_keys_ctx<<<ktiles, 256, 0, s>>>(d_T, n, b.meta, ct, (u32)bits, (u32)ck_key_bits, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
+			if (ck_packed) ck_key_bits = std::min(ck_key_bits, 64 - ck_idx_bits);
+			k_fwd_keys_ctx<<<ktiles, 256, 0, s>>>(d_T, n, b.meta, ct, (u32)bits, (u32)ck_key_bits, ck_packed ? (u32)ck_idx_bits : 0u, b.rb.k[0], b.rb.v[0], b.rb.tile_hist,
 			                                     rs_stride((u32)radix_tiles((size_t)n)), b.err); JP_LAUNCH(c);
 			JP_CUDA(cudaMemcpyAsync(c.h_small + 22, &b.meta->min_depth, sizeof(u32), cudaMemcpyDeviceToHost, s));   // read after the grouping step's sync
 		} else {
@@ -1845,7 +1868,8 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		}
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[1], s));
-		const int cur = radix_sort_pairs(b.rb, 0, n_sorted, 0, ctx_keys ? ck_key_bits : key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
+		const int cur = (ctx_keys && ck_packed) ? radix_sort_pairs(b.rb, 0, n_sorted, ck_idx_bits, ck_idx_bits + ck_key_bits, s, &c.launches, true, /*keys_only=*/true)
+		                                        : radix_sort_pairs(b.rb, 0, n_sorted, 0, ctx_keys ? ck_key_bits : key_bits0, s, &c.launches, /*first_hist_ready=*/!bypass);
 		if (cur < 0) { set_error_detail("radix sort setup failed"); return JP_ERR_CUDA; }
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[2], s));
@@ -1857,8 +1881,13 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		b.AP[1] = reinterpret_cast<u32*>(b.unit[cur ? 3 : 1]);
 		if (!bypass) {
 			// the sorted suffix ids ARE the suffix array
-			b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
-			k_fwd_flags<u64><<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+			if (ctx_keys && ck_packed) {
+				b.SA = b.rb.v[0]; b.VS = b.rb.v[1];
+				k_fwd_unpack<<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, (u32)ck_idx_bits, b.SA, b.F); JP_LAUNCH(c);
+			} else {
+				b.SA = b.rb.v[cur]; b.VS = b.rb.v[cur ^ 1];
+				k_fwd_flags<u64><<<(u32)(((size_t)n + 1023) / 1024), 256, 0, s>>>(b.rb.k[cur], (u32)n, b.F); JP_LAUNCH(c);
+			}
 		} else {
 			// the suffix array is assembled in the other id buffer: sorted suffixes around the buckets, run suffixes inside them
 			b.SA = b.rb.v[cur ^ 1]; b.VS = b.rb.v[cur];
@@ -1888,7 +1917,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 		if (depth0 < 1) depth0 = 1;
 		h = depth0;
 		st->initial_depth = (i32)depth0;
-		if (trace_rounds) fprintf(stderr, "[jp_bwt keys] context-coded: order %u, %u symbols, %d key bits, every key covers >= %lld symbols; active after the sort %u\n", ck_order, ck_S - 1, ck_key_bits, (long long)depth0, A);
+		if (trace_rounds) fprintf(stderr, "[jp_bwt keys] context-coded: order %u, %u symbols, %d key bits%s, every key covers >= %lld symbols; active after the sort %u\n", ck_order, ck_S - 1, ck_key_bits, ck_packed ? " (packed with the position)" : "", (long long)depth0, A);
 	}
 
 	// Periodic repeats: when most of the block is still unsorted, look for a dominant distance between group neighbours.

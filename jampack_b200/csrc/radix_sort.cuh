@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 #ifndef RS_SCATTER_MIN_BLOCKS
 #define RS_SCATTER_MIN_BLOCKS 2
 #endif
-template <typename K>
+// PAIRS = false: the words ARE the records (a key in the high bits, the payload below bit `shift` of the first pass): no
+// value arrays, two thirds of the traffic and of the shared memory.
+template <typename K, bool PAIRS = true>
 __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const K* __restrict__ kin, const u32* __restrict__ vin,
                                                            K* __restrict__ kout, u32* __restrict__ vout,
                                                            const u32* __restrict__ tile_off, u32 stride, u32 n, int shift,
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 		const u32 p = wbase + i * 32 + lane;
 		const bool ok = p < n;
 		key[i] = ok ? kin[p] : (K)~(K)0;  // padding sorts last inside the tile and is never written out
-		val[i] = ok ? vin[p] : 0u;
+		val[i] = (PAIRS && ok) ? vin[p] : 0u;
 	}
 	__syncthreads();
 
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 		const u32 d = rs_digit(key[i], shift);
 		const u32 pos = bin_start[d] + mycnt[d] + rank[i];
 		skey[pos] = key[i];
-		sval[pos] = val[i];
+		if (PAIRS) sval[pos] = val[i];
 	}
 	__syncthreads();
 
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatte
 		const K k = skey[j];
 		const u32 dst = g_off[rs_digit(k, shift)] + j;
 		kout[dst] = k;
-		vout[dst] = sval[j];
+		if (PAIRS) vout[dst] = sval[j];
 		if (dnext) dnext[dst] = (u8)rs_digit(k, next_shift);   // the next pass counts this byte instead of re-reading the key
 	}
 }
@@ -372,9 +374,29 @@ inline size_t radix_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 // holding the result, or a negative error code. launches is incremented per kernel.
 // first_hist_ready: b.tile_hist already holds the tile histogram of the first digit (the producer of the keys made it)
 inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit_hi, cudaStream_t s, int* launches,
-                            bool first_hist_ready = false)
+                            bool first_hist_ready = false, bool keys_only = false)
 {
 	if (n == 0) return cur;
+	if (keys_only) {
+		// the words carry their payload in the bits below bit_lo: classic passes without the value arrays
+		const size_t smem = (size_t)RS_TILE * 8;
+		if (cudaFuncSetAttribute(k_rs_scatter<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
+		for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+			if (shift == bit_lo) {
+				if (!first_hist_ready) { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
+			} else if (b.dnext) { k_rs_hist_bytes<<<tiles, RS_THREADS, 0, s>>>(b.dnext, n, b.tile_hist, stride); *launches += 1; }
+			else { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }
+			k_rs_totals<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
+			k_rs_scan<<<256, 256, 0, s>>>(b.tile_hist, tiles, stride, b.totals);
+			const bool more = shift + 8 < bit_hi;
+			k_rs_scatter<u64, false><<<tiles, RS_THREADS, smem, s>>>(b.k[cur], nullptr, b.k[cur ^ 1], nullptr, b.tile_hist, stride, n, shift,
+			                                                         more ? b.dnext : nullptr, shift + 8);
+			*launches += 3;
+			cur ^= 1;
+		}
+		return cur;
+	}
 	// function attributes are per device; setting one is a host-only call
 	if (cudaFuncSetAttribute(k_rs_scatter<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
 	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);

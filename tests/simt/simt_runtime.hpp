@@ -37,6 +37,8 @@ struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 
 namespace simt {
 extern uint3 g_threadIdx, g_blockIdx;

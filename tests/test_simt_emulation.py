@@ -174,19 +174,22 @@ def _coded_key_blocks():
 
 
 @pytest.mark.parametrize("name", list(_coded_key_blocks()))
-@pytest.mark.parametrize("passes", ["", "4", "8"])
+@pytest.mark.parametrize("passes", ["", "4", "8", "packed"])
 def test_emulated_forward_with_context_coded_keys(emu, orc, name, passes):
     """the initial keys are bit strings of context-chosen alphabetic codewords; the doubling starts from the
     fewest symbols any key covers. Forced on (the default engages it from 1 MiB), with the key length the host picks
-    and with the shortest and longest keys."""
+    and with the shortest and longest keys; "packed": key and position sorted as one 64-bit word."""
     T = np.ascontiguousarray(_coded_key_blocks()[name])
     want = orc.forward(T, "port", prefill=0x5C)
-    keys = ("JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_KEYPASSES", "JP_BWT_FWD_BYPASS")
+    keys = ("JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_KEYPASSES", "JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PACKED")
     saved = {k: os.environ.get(k) for k in keys}
     try:
         os.environ["JP_BWT_FWD_CTXKEYS"] = "1"
         os.environ["JP_BWT_FWD_BYPASS"] = "0"
-        if passes:
+        os.environ["JP_BWT_FWD_PACKED"] = "1" if passes == "packed" else "0"
+        if passes == "packed":
+            os.environ.pop("JP_BWT_FWD_KEYPASSES", None)
+        elif passes:
             os.environ["JP_BWT_FWD_KEYPASSES"] = passes
         else:
             os.environ.pop("JP_BWT_FWD_KEYPASSES", None)
