@@ -24,8 +24,13 @@ cases = [("all-a", np.full(250000, 97, np.uint8), {}), ("zero pages", zero_pages
          ("repetitive / representatives", oracle.gen("repetitive", 400000, 3), {"JP_BWT_FWD_REDUCED": "1"}), ("period 60 / representatives", periodic(300000, 60, 5, 9, 2), {"JP_BWT_FWD_REDUCED": "1"}),
          ("period 300 / repeat lengths", periodic(200000, 300, 2, 5, 4), {"JP_BWT_FWD_PERIODIC": "1", "JP_BWT_FWD_REDUCED": "0"}),
          ("markov2 staged ranks", oracle.gen("markov2", 300000, 1), {"JP_BWT_ISA_STAGE_MIN": "1000", "JP_BWT_ISA_REGION_LOG2": "12"}),
-         ("all-a without bypass (large route, batches)", np.full(200000, 5, np.uint8), {"JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PERIODIC": "0"})]
-keys = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_RUNJUMP", "JP_BWT_FWD_REDUCED", "JP_BWT_FWD_PERIODIC", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2")
+         ("all-a without bypass (large route, batches)", np.full(200000, 5, np.uint8), {"JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PERIODIC": "0"}),
+         ("markov2 coded keys, order 2, packed", oracle.gen("markov2", 300000, 2), {"JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_PACKED": "1"}),
+         ("markov2 coded keys, order 2, pairs", oracle.gen("markov2", 300000 + 77, 2), {"JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_PACKED": "0"}),
+         ("uniform coded keys, order 1, 63 bits", oracle.gen("uniform", 150000, 2), {"JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_KEYPASSES": "8"}),
+         ("dna coded keys, short block", (rng.integers(0, 4, 9000) + 65).astype(np.uint8), {"JP_BWT_FWD_CTXKEYS": "1"})]
+keys = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_RUNJUMP", "JP_BWT_FWD_REDUCED", "JP_BWT_FWD_PERIODIC", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2",
+        "JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_PACKED", "JP_BWT_FWD_KEYPASSES")
 bad = 0
 for name, T, env in cases:
     for k in keys:
