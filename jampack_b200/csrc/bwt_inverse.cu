@@ -922,7 +922,10 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		u8* text = reinterpret_cast<u8*>(b.lf);                             // the LF table is dead once the walk is over
 		// (serialising the walks of the blocks in flight on one GPU behind a host-side gate, so that the other blocks'
 		// table builds, rankings and placements could fill in beside a single DRAM-bound walk, was measured: 35.3-35.6
-		// against 35.7-36.0 GB/s with four blocks in flight -- the hardware's own interleaving is as good)
+		// against 35.7-36.0 GB/s with four blocks in flight -- the hardware's own interleaving is as good; the same chain
+		// built from event dependencies between the callers' streams, no host thread blocking: 37.3 against 36.4.
+		// tools/inflight_phases.py shows why neither helps: with four blocks in flight every kernel of a call stretches,
+		// the walk 1.9x, the others 3-9x -- the kernels take turns on the SMs rather than overlap)
 		k_inv_walk_stream<<<b.wblocks, INV_THREADS, 0, s>>>(b.lf, b.meta, nlen, b.log2m, b.S, b.rec, b.ticket, b.ticket + 2, b.sp, b.err);
 		JP_LAUNCH(c);
 		JP_KCHECK();
