@@ -538,6 +538,24 @@ def test_single_walk_rejects_corrupt_input(jp, orc, single_walk_env):
     assert (jp.inverse(B) == T).all() and jp.last_stats().stream_chunks > 0
 
 
+@pytest.mark.parametrize("kind,n,seed,log2", [("markov2", 5 * MiB + 13, 1, 20), ("uniform", 3 * MiB, 2, 19), ("alla", 2 * MiB, 0, 18)])
+def test_forward_emits_by_text_region(jp, orc, kind, n, seed, log2):
+    """k_fwd_emit_regions (blocks beyond the L2: one sweep over SA per region of the text), here with 256 KiB - 1 MiB regions;
+    the 256 MiB golden block takes the same path with its real 64 MiB regions."""
+    T = orc.gen(kind, n, seed)
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    saved = os.environ.get("JP_BWT_FWD_EMIT_REGION_LOG2")
+    os.environ["JP_BWT_FWD_EMIT_REGION_LOG2"] = str(log2)
+    try:
+        got = jp.forward(T, prefill=0x5C)
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_EMIT_REGION_LOG2", None)
+        else:
+            os.environ["JP_BWT_FWD_EMIT_REGION_LOG2"] = saved
+    assert (got == want).all()
+
+
 def _word_text(n, seed):
     rng = np.random.default_rng(seed)
     words = [bytes(rng.integers(97, 123, int(rng.integers(2, 10)), dtype=np.uint8)) for _ in range(2000)]

@@ -155,6 +155,23 @@ def test_emulated_forward_with_run_bypass(emu, orc, name):
         assert rounds1 < rounds0, (rounds0, rounds1)
 
 
+@pytest.mark.parametrize("kind,n,seed", [("markov2", 30000, 1), ("uniform", 9000 + 119, 2), ("repetitive", 20000, 3)])
+def test_emulated_forward_emits_by_text_region(emu, orc, kind, n, seed):
+    """Blocks beyond the L2 are emitted in one sweep per 64 MiB region of the text (k_fwd_emit_regions); here with 4 KiB regions."""
+    T = orc.gen(kind, n, seed)
+    want = orc.forward(T, "port", prefill=0x5C)
+    saved = os.environ.get("JP_BWT_FWD_EMIT_REGION_LOG2")
+    os.environ["JP_BWT_FWD_EMIT_REGION_LOG2"] = "12"
+    try:
+        rc, got, _, _ = emu.forward(T)
+    finally:
+        if saved is None:
+            os.environ.pop("JP_BWT_FWD_EMIT_REGION_LOG2", None)
+        else:
+            os.environ["JP_BWT_FWD_EMIT_REGION_LOG2"] = saved
+    assert rc == 0 and np.array_equal(got, want)
+
+
 def _coded_key_blocks():
     """Blocks for the context-coded initial keys: both model orders, a compressible order-1 text (63-bit keys), the end of the
     block inside the last keys, a length that is not a multiple of the key tile."""
