@@ -640,6 +640,32 @@ def test_forward_run_bypass_is_bit_exact(jp, orc, kind, n, seed, force):
         assert (jp.inverse(got) == T).all()
 
 
+@pytest.mark.parametrize("p,n,seed", [(300, 3 * MiB, 2), (5000, 4 * MiB + 3, 4), (40000, 6 * MiB, 5), (70000, 6 * MiB, 7), (1021, 8 * MiB, 6)])
+@pytest.mark.parametrize("packed", ["0", "1"])
+def test_forward_periodic_repeats_after_coded_keys(jp, orc, p, n, seed, packed):
+    """A periodic block that does NOT go through its representatives (switched off here; periods beyond the probe's 16 Ki never
+    do): context-coded initial keys, then the detection after the initial step and the repeat-length keys on groups that
+    are finer than "equal h-prefix" (DESIGN 5.4)."""
+    rng = np.random.default_rng(seed)
+    T = np.tile(rng.integers(0, 5, p).astype(np.uint8) + 97, n // p + 1)[:n].copy()
+    T[rng.integers(0, n, 60)] ^= 1
+    want = orc.forward(T, _impl(orc), prefill=0x5C)
+    keys = ("JP_BWT_FWD_REDUCED", "JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_PACKED")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        os.environ.update({"JP_BWT_FWD_REDUCED": "0", "JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_PACKED": packed})
+        got = jp.forward(T, prefill=0x5C)
+        st = jp.last_stats()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert (got == want).all()
+    assert st.period == (p if p <= 65536 else 0), (st.period, st.rounds)     # (the detection looks for distances up to 64 Ki)
+
+
 @pytest.mark.parametrize("kind,n,seed", [("repetitive", 4 * MiB, 3), ("repetitive", 24 * MiB + 5, 9), ("period_12", 3 * MiB, 2), ("period_5000", 6 * MiB, 4),
                                          ("period_2_clean", 2 * MiB, 0), ("runs_in_a_period", 2 * MiB, 1), ("markov2", 2 * MiB, 1)])
 def test_forward_periodic_repeats_are_bit_exact(jp, orc, kind, n, seed):

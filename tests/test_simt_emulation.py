@@ -262,6 +262,28 @@ def test_emulated_forward_with_periodic_repeats(emu, orc, name):
         assert rounds["01"] < rounds["00"], rounds
 
 
+@pytest.mark.parametrize("name", sorted(PERIODIC_CASES))
+def test_emulated_forward_with_periodic_repeats_after_coded_keys(emu, orc, name):
+    """The repeat-length keys on top of the context-coded initial keys: the groups they start from are finer than "equal
+    h-prefix" and h is the fewest symbols any key covers (DESIGN 5.4) -- the pass A / pass B argument only needs that much."""
+    T = PERIODIC_CASES[name](orc)
+    want = orc.forward(T, "port", prefill=0x5C)
+    keys = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_REDUCED", "JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_PACKED")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        os.environ.update({"JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PERIODIC": "1", "JP_BWT_FWD_REDUCED": "0", "JP_BWT_FWD_CTXKEYS": "1"})
+        for packed in ("0", "1"):
+            os.environ["JP_BWT_FWD_PACKED"] = packed
+            rc, got, _, _ = emu.forward(T)
+            assert rc == 0 and (got == want).all(), packed
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 REDUCED_CASES = {"repetitive_200k": lambda orc: orc.gen("repetitive", 200000, 3), "period_300_binary": lambda orc: _periodic(160000, 300, 2, 6, 4),
                  "period_60": lambda orc: _periodic(150000, 60, 5, 10, 3), "period_5000": lambda orc: _periodic(180000, 5000, 4, 3, 8),
                  "period_7_clean": lambda orc: _periodic(140000, 7, 3, 0, 2), "not_periodic": lambda orc: orc.gen("markov2", 140000, 1),
