@@ -126,8 +126,8 @@ typedef struct jp_bwt_stats {
 	int32_t  device;
 	int32_t  kernel_launches;    /* kernels this call launched                                         */
 	int32_t  rounds;             /* forward: prefix-doubling rounds after the initial radix bucketing  */
-	int32_t  symbol_bits;        /* forward: bits per remapped symbol in the initial key               */
-	int32_t  initial_depth;      /* forward: symbols covered by the initial key                        */
+	int32_t  symbol_bits;        /* forward: bits per symbol in the initial key (context-coded keys: the code's mean rate, rounded) */
+	int32_t  initial_depth;      /* forward: symbols EVERY initial key covers = the h the doubling starts from */
 	int32_t  subchains;          /* inverse: sub-chains the 120 decode units were split into           */
 	int32_t  subchain_spacing;   /* inverse: mean sub-chain length (marker spacing m)                  */
 	uint64_t device_bytes;       /* workspace bytes held for this call (excl. caller's in/out)         */

@@ -623,9 +623,21 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_stream(const u32* __re
 }
 
 // Pointer jumping over the packed records; the length field of a record is its own and is carried along.
-__global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int hop_cap)
+// The jumping is asynchronous -- a thread profits from what the threads of its successors have already published -- and
+// how well that works depends on the order the blocks start in. Index order suits lists that run through neighbouring
+// records (single-symbol runs: each block finds the next one at work) and random lists (Markov text: 10.5 record reads per
+// node); on real text, where the LF map sends neighbouring rows to neighbouring rows and whole bundles of lists run in
+// parallel through records nobody has touched yet, it needs 0.83-0.90 ms instead of 0.30. Blocks taken in scattered order
+// (`spread_bits`: block x works on the 256 nodes of block (x * odd) mod 2^spread_bits) do real text in 0.32 ms and a block
+// of one repeated byte in 3.5 ms. So the ranking is two launches: scattered blocks with a budget of four hops per node --
+// after which every record has jumped some nodes ahead, whatever the text -- then index order to the end.
+// Measured (64 MiB, `tools/rank_order_ab.py`): Markov 0.33 (one launch: 0.30), source text 0.34 (0.90), all-`a` 0.29 (0.32),
+// Markov with 0.2-50 % of zero runs 0.31-0.35 (0.30-0.33; scattered alone up to 1.2).
+__global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int hop_cap, int spread_bits,
+                                                         int budget /* hops this launch may take; 0 = to the end, with the final checks */)
 {
-	const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (spread_bits) id = (((blockIdx.x * 0x9E3779B1u) & ((1u << spread_bits) - 1u)) << 8) | threadIdx.x;   // (blocks of 256 consecutive nodes, in scattered order)
 	const u32 nodes = S + N_ANCHOR;
 	if (id >= nodes || *(volatile int*)err != 0) return;
 	volatile u64* vrec = rec;
@@ -635,6 +647,7 @@ __global__ void __launch_bounds__(256) k_inv_rank_packed(u64* __restrict__ rec, 
 	if (nxt == PR_NXT_INVALID) return;
 	int hops = 0;
 	while (nxt < S) {
+		if (budget && hops >= budget) { vrec[id] = pack3(len, nxt, dist); return; }   // (a later launch goes on from here)
 		const u64 o = vrec[nxt];
 		const u32 onxt = pr_nxt(o);
 		dist += pr_dist(o);
@@ -930,8 +943,24 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
-		k_inv_rank_packed<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap);
-		JP_LAUNCH(c);
+		{
+			int spread = bit_length(((u64)nodes + 255) / 256 - 1);
+			if (spread < 1 || spread > 23) spread = 0;
+			// JP_BWT_INV_RANK_PLAN: launches as "<order><hops>" separated by commas, order i (index) or s (scattered blocks),
+			// hops 0 = unbounded; the last launch is always unbounded (it carries the checks).
+			const char* plan = getenv("JP_BWT_INV_RANK_PLAN") ? getenv("JP_BWT_INV_RANK_PLAN") : "s4,i0";
+			for (const char* q = plan; *q;) {
+				const bool scattered = *q == 's' && spread != 0;
+				int hops = atoi(q + 1);
+				const char* comma = strchr(q, ',');
+				if (!comma) hops = 0;
+				const u32 threads = scattered ? (256u << spread) : nodes;
+				k_inv_rank_packed<<<(threads + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap, scattered ? spread : 0, hops);
+				JP_LAUNCH(c);
+				if (!comma) break;
+				q = comma + 1;
+			}
+		}
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);
