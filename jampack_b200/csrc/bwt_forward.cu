@@ -1839,7 +1839,7 @@ static int suffix_sort(Ctx& c, const u8* d_T, i32 n, FwdBuffers& b, cudaStream_t
 	const u32 ck_order = ck_S <= CK_MAX_S2 ? 2u : 1u;
 	const u32 ck_entries = ck_order == 2 ? ck_S * ck_S * ck_S : ck_S * ck_S;
 	bool ctx_keys = !premode && !bypass && n >= (1 << 20);
-	if (const char* e = getenv("JP_BWT_FWD_CTXKEYS")) ctx_keys = !premode && !bypass && atoi(e) != 0 && n >= 4096;
+	if (const char* e = getenv("JP_BWT_FWD_CTXKEYS")) ctx_keys = !premode && !bypass && atoi(e) != 0 && n >= 256;
 	if (ctx_keys && Arena::align(((size_t)ck_entries + 31) / 32 * 4) + Arena::align((size_t)ck_entries * 4) + (size_t)ck_entries * 2 > 2 * b.usz) ctx_keys = false;
 	int ck_key_bits = 8 * std::min(8, std::max(4, (bit_length((u64)n) + 13 + 7) / 8));
 	if (const char* e = getenv("JP_BWT_FWD_KEYPASSES")) ck_key_bits = 8 * std::min(8, std::max(3, atoi(e)));

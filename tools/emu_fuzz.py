@@ -13,7 +13,8 @@ import numpy as np  # noqa: E402
 import oracle  # noqa: E402
 import simt  # noqa: E402
 
-SWITCHES = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP", "JP_BWT_FWD_REDUCED", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2", "JP_BWT_INV_SINGLE", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM")
+SWITCHES = ("JP_BWT_FWD_BYPASS", "JP_BWT_FWD_PERIODIC", "JP_BWT_FWD_RUNJUMP", "JP_BWT_FWD_REDUCED", "JP_BWT_ISA_STAGE_MIN", "JP_BWT_ISA_REGION_LOG2", "JP_BWT_INV_SINGLE", "JP_BWT_INV_LOG2M", "JP_BWT_INV_WBLOCKS_PER_SM",
+            "JP_BWT_FWD_CTXKEYS", "JP_BWT_FWD_PACKED", "JP_BWT_FWD_KEYPASSES", "JP_BWT_FWD_EMIT_REGION_LOG2", "JP_BWT_INV_RANK_PLAN")
 
 
 def block(rng, n):
@@ -57,7 +58,9 @@ def main():
         want = oracle.forward(T, "port", prefill=0x5C)
         if not big:                                        # the forward is slow under emulation: small blocks only
             for fv in ({"JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PERIODIC": "0"}, {"JP_BWT_FWD_BYPASS": "1", "JP_BWT_FWD_RUNJUMP": "1"}, {"JP_BWT_FWD_PERIODIC": "1"},
-                       {"JP_BWT_FWD_BYPASS": "1", "JP_BWT_FWD_PERIODIC": "1", "JP_BWT_ISA_STAGE_MIN": "100", "JP_BWT_ISA_REGION_LOG2": str(6 + c % 5)}):
+                       {"JP_BWT_FWD_BYPASS": "1", "JP_BWT_FWD_PERIODIC": "1", "JP_BWT_ISA_STAGE_MIN": "100", "JP_BWT_ISA_REGION_LOG2": str(6 + c % 5)},
+                       {"JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_PACKED": str(c & 1), "JP_BWT_FWD_PERIODIC": str((c >> 1) & 1), "JP_BWT_FWD_EMIT_REGION_LOG2": str(9 + c % 3)},
+                       {"JP_BWT_FWD_CTXKEYS": "1", "JP_BWT_FWD_BYPASS": "0", "JP_BWT_FWD_KEYPASSES": str(4 + c % 5)}):
                 for k in SWITCHES:
                     os.environ.pop(k, None)
                 os.environ.update(fv)
@@ -66,7 +69,7 @@ def main():
                     fails += 1; print(f"case {c}: forward mismatch {fv} n={T.size} rc={rc}", flush=True)
         variants = [{}]
         if big:
-            variants += [{"JP_BWT_INV_SINGLE": "1"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_LOG2M": "4"}]
+            variants += [{"JP_BWT_INV_SINGLE": "1"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_LOG2M": "4"}, {"JP_BWT_INV_SINGLE": "1", "JP_BWT_INV_RANK_PLAN": ["i0", "s0", "s1,i2,s0"][c % 3]}]
         for v in variants:
             for k in SWITCHES:
                 os.environ.pop(k, None)
