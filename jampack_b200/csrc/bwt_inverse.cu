@@ -390,9 +390,12 @@ __global__ void __launch_bounds__(INV_THREADS) k_inv_walk_len(const u32* __restr
 // start lies the start of `next`"; replacing it by (next.next, dist + next.dist) keeps that true whichever
 // version of next's record was read, so no double buffering or rounds are needed: 8-byte loads/stores are
 // single transactions. Anchors (ids >= S) absorb.
-__global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int check_units, int hop_cap)
+// (spread_bits, budget: the launch plan described at k_inv_rank_packed)
+__global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, i32 step, int* __restrict__ err, int check_units, int hop_cap,
+                                                  int spread_bits, int budget)
 {
-	const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (spread_bits) id = (((blockIdx.x * 0x9E3779B1u) & ((1u << spread_bits) - 1u)) << 8) | threadIdx.x;
 	const u32 nodes = S + N_ANCHOR;
 	if (id >= nodes) return;
 	volatile u64* vrec = rec;
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(256) k_inv_rank(u64* __restrict__ rec, u32 S, 
 	if (nxt == REC_INVALID) return;
 	int hops = 0;
 	while (nxt < S) {
+		if (budget && hops >= budget) { vrec[id] = pack_rec(nxt, dist); return; }
 		const u64 o = vrec[nxt];
 		nxt = (u32)(o >> 32);
 		dist += (u32)o;
@@ -793,6 +797,26 @@ static int walk_flags()
 	return 0;   // measured on B200: the L2 policies change nothing (3.73 ms without, 3.82-3.91 ms with)
 }
 
+// Launch plan of the ranking kernels. JP_BWT_INV_RANK_PLAN: launches as "<order><hops>" separated by commas, order i
+// (index) or s (scattered blocks), hops 0 = unbounded; the last launch is always unbounded (it carries the checks).
+template <typename Launch>
+static int rank_plan(Ctx& c, u32 nodes, Launch launch)
+{
+	int spread = bit_length(((u64)nodes + 255) / 256 - 1);
+	if (spread < 1 || spread > 23) spread = 0;
+	const char* plan = getenv("JP_BWT_INV_RANK_PLAN") ? getenv("JP_BWT_INV_RANK_PLAN") : "s4,i0";
+	for (const char* q = plan; *q;) {
+		const bool scattered = *q == 's' && spread != 0;
+		const char* comma = strchr(q, ',');
+		const int hops = comma ? atoi(q + 1) : 0;
+		launch(scattered ? (1u << spread) : (nodes + 255) / 256, scattered ? spread : 0, hops);
+		JP_LAUNCH(c);
+		if (!comma) break;
+		q = comma + 1;
+	}
+	return JP_OK;
+}
+
 static int walker_blocks(Ctx& c, const void* kernel)
 {
 	int per_sm = 0;
@@ -943,24 +967,9 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		JP_LAUNCH(c);
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
-		{
-			int spread = bit_length(((u64)nodes + 255) / 256 - 1);
-			if (spread < 1 || spread > 23) spread = 0;
-			// JP_BWT_INV_RANK_PLAN: launches as "<order><hops>" separated by commas, order i (index) or s (scattered blocks),
-			// hops 0 = unbounded; the last launch is always unbounded (it carries the checks).
-			const char* plan = getenv("JP_BWT_INV_RANK_PLAN") ? getenv("JP_BWT_INV_RANK_PLAN") : "s4,i0";
-			for (const char* q = plan; *q;) {
-				const bool scattered = *q == 's' && spread != 0;
-				int hops = atoi(q + 1);
-				const char* comma = strchr(q, ',');
-				if (!comma) hops = 0;
-				const u32 threads = scattered ? (256u << spread) : nodes;
-				k_inv_rank_packed<<<(threads + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap, scattered ? spread : 0, hops);
-				JP_LAUNCH(c);
-				if (!comma) break;
-				q = comma + 1;
-			}
-		}
+		JP_TRY(rank_plan(c, nodes, [&](u32 blocks, int spread, int budget) {
+			k_inv_rank_packed<<<blocks, 256, 0, s>>>(b.rec, b.S, step, b.err, hop_cap, spread, budget);
+		}));
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		k_inv_clear_text<<<c.sm_count * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(text), (u32)(((size_t)nlen + 15) / 16), b.err); JP_LAUNCH(c);
@@ -989,7 +998,9 @@ int inverse_device(Ctx& c, const u8* d_in, i32 len_with_trailer, u8* d_out, cuda
 		JP_CUDA(cudaEventRecord(c.ev[3], s));
 		// (a two-level scheme -- majors walk to majors, jump, hand down -- was tried: 0.86 ms against 0.28 ms; the
 		// dependent record-to-record walks are latency-bound, the flat jumping is not)
-		k_inv_rank<<<(nodes + 255) / 256, 256, 0, s>>>(b.rec, b.S, step, b.err, 1, hop_cap); JP_LAUNCH(c);
+		JP_TRY(rank_plan(c, nodes, [&](u32 blocks, int spread, int budget) {
+			k_inv_rank<<<blocks, 256, 0, s>>>(b.rec, b.S, step, b.err, 1, hop_cap, spread, budget);
+		}));
 		JP_KCHECK();
 		JP_CUDA(cudaEventRecord(c.ev[4], s));
 		JP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nlen, s));               // shared words of neighbouring sub-chains are merged by RED.OR
