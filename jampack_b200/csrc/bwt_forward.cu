@@ -1148,28 +1148,42 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_seg_sort(const u32* __restric
 		pk[i] = f | (b << 13) | (hl << 26);
 	}
 	__syncthreads();
+	// The warp totals, in (row, warp) order, are one sequence of 128: warp 0 turns wf into "latest head before this
+	// (row, warp)", warp 1 turns wb into "first group end after it" -- 4 entries per lane and one warp scan each -- and
+	// every thread then reads its 16 entries instead of looping over all 128 twice.
+	constexpr int SG_NW = SG_THREADS / 32, SG_TOT = SG_ITEMS * SG_NW;
+	static_assert(SG_TOT == 128, "4 warp totals per lane");
+	if (w == 0) {
+		u32* f1 = &wf[0][0];
+		u32 v[4], run = 0;
+		#pragma unroll
+		for (int q = 0; q < 4; q++) { v[q] = f1[lane * 4 + q]; run = max(run, v[q]); }
+		const u32 inc = (u32)warp_incl_max((i32)run);
+		u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+		if (lane == 0) ex = 0;
+		#pragma unroll
+		for (int q = 0; q < 4; q++) { f1[lane * 4 + q] = ex; ex = max(ex, v[q]); }
+	} else if (w == 1) {
+		u32* b1 = &wb[0][0];
+		u32 v[4], run = 0x1fffu;
+		#pragma unroll
+		for (int q = 0; q < 4; q++) { v[q] = b1[SG_TOT - 1 - (lane * 4 + q)]; run = min(run, v[q]); }
+		u32 inc = run;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = min(inc, x); }
+		u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+		if (lane == 0) ex = 0x1fffu;
+		#pragma unroll
+		for (int q = 0; q < 4; q++) { b1[SG_TOT - 1 - (lane * 4 + q)] = ex; ex = min(ex, v[q]); }
+	}
+	__syncthreads();
 	int big = 0;
-	{
-		u32 run = 0;
-		#pragma unroll
-		for (int i = 0; i < SG_ITEMS; i++) {
-			u32 pm = run, tm = run;
-			#pragma unroll
-			for (int k = 0; k < SG_THREADS / 32; k++) { const u32 a = wf[i][k]; if (k < w) pm = max(pm, a); tm = max(tm, a); }
-			pk[i] = (pk[i] & ~0x1fffu) | max(pk[i] & 0x1fffu, pm);
-			run = tm;
-		}
-		run = 0x1fffu;
-		#pragma unroll
-		for (int i = SG_ITEMS - 1; i >= 0; i--) {
-			u32 pm = run, tm = run;
-			#pragma unroll
-			for (int k = SG_THREADS / 32 - 1; k >= 0; k--) { const u32 a = wb[i][k]; if (k > w) pm = min(pm, a); tm = min(tm, a); }
-			const u32 ge = min((pk[i] >> 13) & 0x1fffu, pm);
-			pk[i] = (pk[i] & ~(0x1fffu << 13)) | (ge << 13);
-			if ((pk[i] >> 28) & 1u) big |= (ge - (pk[i] & 0x1fffu) > SG_PAIR_MAX);
-			run = tm;
-		}
+	#pragma unroll
+	for (int i = 0; i < SG_ITEMS; i++) {
+		const u32 gs = max(pk[i] & 0x1fffu, wf[i][w]);
+		const u32 ge = min((pk[i] >> 13) & 0x1fffu, wb[i][w]);
+		pk[i] = (pk[i] & ~0x3ffffffu) | gs | (ge << 13);
+		if ((pk[i] >> 28) & 1u) big |= (ge - gs > SG_PAIR_MAX);
 	}
 	if (__syncthreads_or(big)) {                        // a long group: the radix kernel takes this tile
 		if (t == 0) queue[atomicAdd(counters + 3, 1u)] = blockIdx.x;
