@@ -144,10 +144,13 @@ __global__ void __launch_bounds__(256) k_rs_scan(u32* __restrict__ tile_hist, u3
 #ifndef RS_SCATTER_MIN_BLOCKS
 #define RS_SCATTER_MIN_BLOCKS 2
 #endif
+#ifndef RS_SCATTER_MIN_BLOCKS_KEYS
+#define RS_SCATTER_MIN_BLOCKS_KEYS 4          // keys-only records: no value registers, 64 registers without spills, 32 KB of tile
+#endif
 // PAIRS = false: the words ARE the records (a key in the high bits, the payload below bit `shift` of the first pass): no
 // value arrays, two thirds of the traffic and of the shared memory.
 template <typename K, bool PAIRS = true>
-__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_rs_scatter(const K* __restrict__ kin, const u32* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, PAIRS ? RS_SCATTER_MIN_BLOCKS : RS_SCATTER_MIN_BLOCKS_KEYS) k_rs_scatter(const K* __restrict__ kin, const u32* __restrict__ vin,
                                                            K* __restrict__ kout, u32* __restrict__ vout,
                                                            const u32* __restrict__ tile_off, u32 stride, u32 n, int shift,
                                                            u8* __restrict__ dnext = nullptr, int next_shift = 0)
