@@ -1481,7 +1481,7 @@ static size_t fwd_bytes(i32 n, bool own_flags)
 {
 	const size_t N = (size_t)n;
 	const size_t rtiles = radix_tiles(N), gtiles = (N + GS_TILE - 1) / GS_TILE;
-	return 6 * Arena::align((N + 2) * 4) + Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) + Arena::align((8 * 256 + 64) * 4) +
+	return 6 * Arena::align((N + 2) * 4) + Arena::align((rtiles + 4) * 256 * 4) + Arena::align(256 * 4) +
 	       Arena::align(gtiles * sizeof(GAgg)) + Arena::align(sizeof(FwdMeta)) + Arena::align(64) + Arena::align(64) +
 	       5 * Arena::align((N / SG_WIN + 16) * 4) + (own_flags ? Arena::align(N + 64) : 0);
 }
@@ -1500,13 +1500,8 @@ static int fwd_alloc(Ctx& c, i32 n, FwdBuffers& b, u8* d_flags)
 	if (const char* e = getenv("JP_BWT_ISA_REGION_LOG2")) b.isa_region_log2 = atoi(e);
 	b.rb.tile_hist = arena_take<u32>(c, (rtiles + 4) * 256);
 	b.rb.totals = arena_take<u32>(c, 256);
-	b.rb.os_state = arena_take<u32>(c, 8 * 256 + 64);
 	b.F = d_flags ? d_flags : arena_take<u8>(c, N + 64);
 	b.rb.dnext = getenv("JP_BWT_RADIX_NO_DIGIT_BYTES") ? nullptr : b.F;
-	// Measured on B200 (64 M pairs, 8 passes): three-kernel passes 5.07 ms, one-sweep (all digits counted in one read of
-	// the keys + 8 look-back passes) 6.18 ms -- with ~440 tiles in flight the per-digit look-back chain costs more than
-	// the key re-read it saves, so the classic pass is the default.
-	b.rb.classic = getenv("JP_BWT_RADIX_ONESWEEP") == nullptr;
 	b.queue = arena_take<u32>(c, N / SG_WIN + 16);
 	b.win_first = arena_take<u32>(c, N / SG_WIN + 16); b.win_large = arena_take<u32>(c, N / SG_WIN + 16);
 	b.lg_head = arena_take<u32>(c, N / SG_WIN + 16); b.lg_off = arena_take<u32>(c, N / SG_WIN + 16);

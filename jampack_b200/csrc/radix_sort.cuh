@@ -5,7 +5,8 @@
 // One pass = per-tile digit histogram -> per-digit exclusive scan over tiles -> ranked scatter. The scatter
 // ranks keys inside a warp with match.any (no atomics, stable), re-orders the tile in shared memory so that
 // every digit's run leaves as coalesced stores, and adds the tile's global offsets.
-// No inter-block dependency (no look-back spin) -- a pass cannot hang.
+// No inter-block dependency (no look-back spin) -- a pass cannot hang. (A one-sweep variant with decoupled look-back was
+// built and measured in round 1: 6.2 ms against 5.1 ms for 8 passes over 64 M pairs; removed.)
 #pragma once
 #include "common.cuh"
 
@@ -228,147 +229,12 @@ __global__ void __launch_bounds__(RS_THREADS, PAIRS ? RS_SCATTER_MIN_BLOCKS : RS
 	}
 }
 
-// ---- single-pass-per-digit variant ("onesweep": chained scan with decoupled look-back) --------------------
-// The three-kernel pass above reads the keys twice (histogram, scatter). Here one kernel does a whole digit:
-// blocks take tiles in ticket order, rank their keys, publish the tile's digit counts as an AGGREGATE word,
-// sum their predecessors' words backwards until they meet an inclusive PREFIX word, publish their own prefix
-// and scatter. The global histogram of every digit position (which does not depend on the order of the keys) is
-// counted once, up front, in a single read of the keys (k_os_count_all). A tile's predecessors hold earlier tickets, so they are running or done and publish before
-// they wait: the chain cannot deadlock; a spin cap turns any surprise into an error flag instead of a hang.
-constexpr u32 OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 1u << 31, OS_VALUE_MASK = (1u << 30) - 1;
-constexpr u32 OS_SPIN_CAP = 1u << 26;
-
-__device__ __forceinline__ void os_store(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ u32 os_load(const u32* p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-
-// global digit counts of EVERY digit position in one read of the keys: ghist[pass][256]
-constexpr int OS_MAX_PASSES = 8;
-__global__ void __launch_bounds__(RS_THREADS) k_os_count_all(const u64* __restrict__ keys, u32 n, int bit_lo, int passes, u32* __restrict__ ghist)
-{
-	__shared__ u32 h[OS_MAX_PASSES][256];
-	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-	for (int i = t; i < OS_MAX_PASSES * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
-	__syncthreads();
-	const u32 lt = lanemask_lt();
-	for (u32 tile = blockIdx.x; (u64)tile * RS_TILE < n; tile += gridDim.x) {
-		const u32 base = tile * RS_TILE + w * (32 * RS_ITEMS);
-		#pragma unroll 4
-		for (int i = 0; i < RS_ITEMS; i++) {
-			const u32 p = base + i * 32 + lane;
-			const bool ok = p < n;
-			const u64 k = ok ? keys[p] : 0ull;
-			const u32 vmask = __ballot_sync(0xffffffffu, ok);
-			for (int q = 0; q < passes; q++) {
-				const u32 d = rs_digit(k, bit_lo + 8 * q);
-				const u32 peers = match_any8_adaptive(d) & vmask;
-				if (ok && (peers & lt) == 0) atomicAdd(&h[q][d], (u32)__popc(peers));
-			}
-		}
-	}
-	__syncthreads();
-	for (int q = 0; q < passes; q++) { const u32 c = h[q][t]; if (c) atomicAdd(&ghist[q * 256 + t], c); }
-}
-
-__global__ void __launch_bounds__(RS_THREADS, RS_SCATTER_MIN_BLOCKS) k_os_pass(const u64* __restrict__ kin, const u32* __restrict__ vin,
-                                                        u64* __restrict__ kout, u32* __restrict__ vout, u32 n, int shift,
-                                                        const u32* __restrict__ ghist,
-                                                        u32* __restrict__ lookback, u32* __restrict__ ticket, int* __restrict__ err)
-{
-	extern __shared__ __align__(16) u8 rs_smem[];
-	u64* skey = reinterpret_cast<u64*>(rs_smem);
-	u32* sval = reinterpret_cast<u32*>(rs_smem + (size_t)RS_TILE * 8);
-	__shared__ u32 wcnt[RS_WARPS][256];
-	__shared__ u32 bin_start[256];
-	__shared__ u32 g_off[256];
-	__shared__ u32 ws[32];
-	__shared__ u32 s_tile;
-
-	const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-	const u32 lt = lanemask_lt();
-	if (t == 0) s_tile = atomicAdd(ticket, 1u);
-	for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
-	__syncthreads();
-	const u32 tile = s_tile;
-	const u32 tile_base = tile * RS_TILE;
-	const u32 valid = min((u32)RS_TILE, n - tile_base);
-
-	u64 key[RS_ITEMS];
-	u32 val[RS_ITEMS];
-	const u32 wbase = tile_base + w * (32 * RS_ITEMS);
-	#pragma unroll
-	for (int i = 0; i < RS_ITEMS; i++) {
-		const u32 p = wbase + i * 32 + lane;
-		const bool ok = p < n;
-		key[i] = ok ? kin[p] : ~0ull;
-		val[i] = ok ? vin[p] : 0u;
-	}
-	u32 rank[RS_ITEMS];
-	u32* mycnt = wcnt[w];
-	#pragma unroll
-	for (int i = 0; i < RS_ITEMS; i++) {
-		const u32 d = rs_digit(key[i], shift);
-		const u32 peers = match_any8_adaptive(d);
-		const u32 below = __popc(peers & lt);
-		u32 before = 0;
-		if (below == 0) { before = mycnt[d]; mycnt[d] = before + __popc(peers); }
-		before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
-		rank[i] = before + below;
-		__syncwarp();
-	}
-	__syncthreads();
-
-	// digit t: counts over warps (-> exclusive per warp), the tile's count, the digit's global base
-	u32 run = 0;
-	#pragma unroll
-	for (int k = 0; k < RS_WARPS; k++) { const u32 v = wcnt[k][t]; wcnt[k][t] = run; run += v; }
-	u32 cnt = run;
-	if (t == 255) cnt -= (u32)RS_TILE - valid;          // the padding keys all carry digit 255 and are not real
-	// publish, then look back
-	u32 excl = 0;
-	if (tile == 0) os_store(lookback + t, cnt | OS_FLAG_PREFIX);
-	else {
-		os_store(lookback + (size_t)tile * 256 + t, cnt | OS_FLAG_AGG);
-		u32 spins = 0;
-		for (u32 i = tile - 1;; ) {
-			const u32 sv = os_load(lookback + (size_t)i * 256 + t);
-			if ((sv >> 30) == 0) { if (++spins > OS_SPIN_CAP) { dev_fail(err, DE_FWD_ROUNDS); break; } continue; }
-			excl += sv & OS_VALUE_MASK;
-			if (sv & OS_FLAG_PREFIX) break;
-			i--;
-		}
-		os_store(lookback + (size_t)tile * 256 + t, ((excl + cnt) & OS_VALUE_MASK) | OS_FLAG_PREFIX);
-	}
-	u32 total;
-	const u32 dig_incl = block_incl_sum(ghist[t], ws, &total);          // global exclusive base of digit t
-	const u32 inc = block_incl_sum(run, ws, &total);
-	bin_start[t] = inc - run;
-	g_off[t] = (dig_incl - ghist[t]) + excl - (inc - run);
-	__syncthreads();
-
-	#pragma unroll
-	for (int i = 0; i < RS_ITEMS; i++) {
-		const u32 d = rs_digit(key[i], shift);
-		const u32 pos = bin_start[d] + mycnt[d] + rank[i];
-		skey[pos] = key[i];
-		sval[pos] = val[i];
-	}
-	__syncthreads();
-	for (u32 j = t; j < valid; j += RS_THREADS) {
-		const u64 k = skey[j];
-		const u32 dst = g_off[rs_digit(k, shift)] + j;
-		kout[dst] = k;
-		vout[dst] = sval[j];
-	}
-}
-
 struct RadixBuffers {
 	u64* k[2]; u32* v[2];
-	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries; the look-back words of the one-sweep passes
+	u32* tile_hist;   // 256 rows of rs_stride(ceil(n / RS_TILE)) entries
 	u32* totals;      // 256
 	u8*  dnext;       // n bytes (or null): digit of the next pass, written by the scatter, read by k_rs_hist_bytes
-	u32* os_state;    // one-sweep: digit histograms of every pass [8][256], then the tile ticket
 	int* err;
-	bool classic;     // three-kernel passes (A/B switch, and blocks of 2^30 keys or more)
 };
 
 inline size_t radix_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
@@ -403,25 +269,6 @@ inline int radix_sort_pairs(RadixBuffers& b, int cur, u32 n, int bit_lo, int bit
 	// function attributes are per device; setting one is a host-only call
 	if (cudaFuncSetAttribute(k_rs_scatter<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
 	const u32 tiles = (u32)radix_tiles(n), stride = rs_stride(tiles);
-	if (!b.classic && n < (1u << 30)) {
-		if (cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_SCATTER) != cudaSuccess) return -1;
-		const int passes = (bit_hi - bit_lo + 7) / 8;
-		if (passes > OS_MAX_PASSES) return -1;
-		u32* ghist = b.os_state;                        // [passes][256]
-		u32* ticket = b.os_state + OS_MAX_PASSES * 256;
-		cudaMemsetAsync(b.os_state, 0, (OS_MAX_PASSES * 256 + 16) * sizeof(u32), s);
-		k_os_count_all<<<min(tiles, 148u * 8u), RS_THREADS, 0, s>>>(b.k[cur], n, bit_lo, passes, ghist);
-		*launches += 1;
-		for (int q = 0; q < passes; q++) {
-			cudaMemsetAsync(b.tile_hist, 0, (size_t)tiles * 256 * sizeof(u32), s);
-			cudaMemsetAsync(ticket, 0, sizeof(u32), s);
-			k_os_pass<<<tiles, RS_THREADS, RS_SMEM_SCATTER, s>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n, bit_lo + 8 * q,
-			                                                     ghist + q * 256, b.tile_hist, ticket, b.err);
-			*launches += 1;
-			cur ^= 1;
-		}
-		return cur;
-	}
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
 		if (shift == bit_lo) {
 			if (!first_hist_ready) { k_rs_hist<u64><<<tiles, RS_THREADS, 0, s>>>(b.k[cur], n, shift, b.tile_hist, stride); *launches += 1; }

@@ -463,7 +463,7 @@ def test_corrupted_bwt_bytes_never_hang_or_crash(jp, orc):
 @pytest.fixture
 def single_walk_env():
     """JP_BWT_INV_* are read per call; restore them whatever the test does."""
-    keys = ("JP_BWT_INV_SINGLE", "JP_BWT_INV_STREAM_CAP", "JP_BWT_INV_WBLOCKS_PER_SM")
+    keys = ("JP_BWT_INV_SINGLE", "JP_BWT_INV_STREAM_CAP", "JP_BWT_INV_WBLOCKS_PER_SM", "JP_BWT_INV_FLAGS", "JP_BWT_INV_LOG2M")
     saved = {k: os.environ.get(k) for k in keys}
     yield os.environ
     for k, v in saved.items():
@@ -484,6 +484,14 @@ def test_single_walk_inverse_matches_two_pass(jp, orc, single_walk_env, kind, n,
     single_walk_env["JP_BWT_INV_SINGLE"] = "0"
     two_pass = jp.inverse(B)
     assert jp.last_stats().stream_chunks == 0
+    # the measured-and-rejected variants that are still switches (cache hints of the two-pass walkers, marker spacing)
+    for flags, log2m in (("1", None), ("2", None), ("3", "5"), (None, "3")):
+        if flags is not None:
+            single_walk_env["JP_BWT_INV_FLAGS"] = flags
+        if log2m is not None:
+            single_walk_env["JP_BWT_INV_LOG2M"] = log2m
+        assert (jp.inverse(B) == T).all(), (flags, log2m)
+        single_walk_env.pop("JP_BWT_INV_FLAGS", None); single_walk_env.pop("JP_BWT_INV_LOG2M", None)
     single_walk_env["JP_BWT_INV_SINGLE"] = "1"
     one = jp.inverse(B)
     st = jp.last_stats()
