@@ -198,10 +198,10 @@ __global__ void __launch_bounds__(256) k_fwd_keys(const u8* __restrict__ T, i32 
 // rounds do not mind: a group only ever has to consist of suffixes that agree on h symbols and to sit where the true
 // order puts it. The code tables come from one pass over the text: which (context, symbol) pairs occur at all (exact, a
 // bitmap) and how often (counted on a sample); a pair that does not occur gets no codeword, so the frequent successors
-// of a context keep codewords of about -log2 p bits. With a key bit worth about a bit of information, 6 radix passes
-// cover what 8 did (key_bits = 48) and the first doubling round finds a few per cent of the block still unsorted
-// instead of half of it.
-constexpr int CK_LMAX = 12;                       // longest codeword (length-limited so that a key covers >= order + 4 symbols)
+// of a context keep codewords of about -log2 p bits. With a key bit worth about a bit of information, log2 n + 13 key
+// bits (5 radix passes for a 64 MiB block, where the mixed-radix key needs 8) leave the first doubling round a few per
+// cent of the block instead of half of it; and keys that short fit into one 64-bit word with the position (host side).
+constexpr int CK_LMAX = 12;                       // longest codeword (length-limited: a key always covers a few symbols beyond the fixed ones)
 constexpr int CK_LA = 72;                         // symbols read beyond the tile: a codeword has >= 1 bit, a key < 64
 constexpr u32 CK_MAX_S2 = 80;                     // order 2 up to 79 symbols + end: 80^3 table entries
 struct CtxTabs { u32* present; u32* counts; u16* table; u32 S, order, entries; };
