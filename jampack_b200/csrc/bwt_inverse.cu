@@ -805,15 +805,17 @@ static int rank_plan(Ctx& c, u32 nodes, Launch launch)
 	int spread = bit_length(((u64)nodes + 255) / 256 - 1);
 	if (spread < 1 || spread > 23) spread = 0;
 	const char* plan = getenv("JP_BWT_INV_RANK_PLAN") ? getenv("JP_BWT_INV_RANK_PLAN") : "s4,i0";
-	for (const char* q = plan; *q;) {
+	bool complete = false;
+	for (const char* q = plan; *q && !complete;) {
 		const bool scattered = *q == 's' && spread != 0;
 		const char* comma = strchr(q, ',');
-		const int hops = comma ? atoi(q + 1) : 0;
+		const int hops = (comma && comma[1]) ? std::max(0, atoi(q + 1)) : 0;
 		launch(scattered ? (1u << spread) : (nodes + 255) / 256, scattered ? spread : 0, hops);
 		JP_LAUNCH(c);
-		if (!comma) break;
-		q = comma + 1;
+		complete = hops == 0;
+		q = comma ? comma + 1 : q + strlen(q);
 	}
+	if (!complete) { launch((nodes + 255) / 256, 0, 0); JP_LAUNCH(c); }      // (whatever the plan said: the ranking ends with an unbounded launch)
 	return JP_OK;
 }
 
